@@ -1,0 +1,423 @@
+#!/usr/bin/env python
+"""bench.py — interpolated frames/s of the optical-flow interpolation hot path on B200.
+
+Workload (BASELINE.json configs[2], the configuration the metric is quoted on): 3840x2160 P010 HDR,
+23.976 -> 144 fps, full-resolution flow, search radius R = 16 (where the reference's auto-tuner saturates
+on a fast GPU), deltaScalar 8, neighborScalar 6, levels 0/255, BlendedFrame output.
+
+A step = one source frame through the reference's call sequence (HopperRender.cpp:953-1186):
+updateFrame + calculateOpticalFlow + N x warpFrames, N from the filter's own schedule (6, occasionally 7).
+  value : device-resident — frames already in HBM (a ring larger than L2), outputs left in HBM.
+  e2e   : the same through the public blocking API with pinned HOST buffers: H2D of the source frame and
+          a D2H downloadFrame of every output frame inside the timed region.
+One process per GPU; each rank runs its own independent stream (no data-path collective) => weak scaling.
+
+`--impl reference` times the reference's algorithm on the host CPU cores (the oracle port of the OpenCL
+kernels, OpenMP on all cores; the reference itself needs an OpenCL device, which this box lacks) on a
+bounded sample of the same workload.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+WORKLOADS = {
+    # name: (W, H, hdr, maxCalcRes, target_frame_time)
+    "cfg3": dict(W=3840, H=2160, hdr=True, maxres=2160, target=69444, desc="3840x2160 P010 HDR 23.976->144 fps, full-resolution flow"),
+    "cfg2": dict(W=1920, H=1080, hdr=False, maxres=540, target=69444, desc="1920x1080 NV12 SDR 23.976->144 fps, half-resolution flow"),
+    "cfg1": dict(W=1920, H=1080, hdr=False, maxres=270, target=166667, desc="1920x1080 NV12 SDR 24->60 fps, 270p flow"),
+}
+SEARCH_RADIUS = 16
+METRIC = "interpolated frames/s at 4K P010 (flow + warp, R=16)"
+UNIT = "frames/s"
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            return json.load(f), "measured"
+    return {"hbm_gbs": 6650.0}, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)."""
+    Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index):
+        self.index = index
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._pump, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            c = [x.strip() for x in r.split(",")]
+            if len(c) < 7:
+                continue
+            try:
+                sm.append(float(c[0]))
+                mx.append(float(c[1]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), c[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def dist_env():
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    return rank, world, local
+
+
+def algorithmic_bytes(wl):
+    """F = 1.5*W*H*bpp, L = lw*lh; warp (mode 2) = 3F + 4L per launch."""
+    bpp = 2 if wl["hdr"] else 1
+    rs = 0
+    while (wl["H"] >> rs) > wl["maxres"]:
+        rs += 1
+    lw, lh = -(-wl["W"] // (1 << rs)), -(-wl["H"] // (1 << rs))
+    F = wl["W"] * wl["H"] * 3 // 2 * bpp
+    L = lw * lh
+    ws = 1
+    while ws < max(lw, lh):
+        ws <<= 1
+    iters = max(ws // 2, 1).bit_length() - 1
+    return dict(F=F, L=L, warp=3 * F + 4 * L, blur=8 * L, copy=2 * F, passes=2 * iters, absdiff=3 * SEARCH_RADIUS * L * 2 * iters, lw=lw, lh=lh)
+
+
+# ------------------------------------------------------------------------------------------------------
+# reference arm / cpu_baseline: the oracle port on the host cores
+# ------------------------------------------------------------------------------------------------------
+def cpu_sample_rows(wl, budget_s):
+    """Rows of a full-width band of the workload frame whose flow + warps cost about budget_s on this host."""
+    from hopperrender_b200 import synth
+    from oracle import OracleCalc
+    W, hdr = wl["W"], wl["hdr"]
+    probe = 128
+    o = OracleCalc(probe, W, 0, 0, 8, 6, 0.0, 255.0, probe, hdr)
+    o.setParams(searchRadius=SEARCH_RADIUS)
+    fr = [synth.make_frame(W, probe, t, hdr=hdr, noise=False) for t in range(3)]
+    for f in fr:
+        o.updateFrame(f)
+    t0 = time.perf_counter()
+    o.calculateOpticalFlow()
+    for _ in range(6):
+        o.warpFrames(0.5, 2)
+    dt = time.perf_counter() - t0
+    o.close()
+    rows = int(probe * budget_s / max(dt, 1e-6))
+    rows = max(64, min(wl["H"], rows // 16 * 16))
+    return rows
+
+
+def cpu_step_runner(wl, rows):
+    """Returns (fn, n_out): fn() runs one source-frame step (update + flow + N warps + downloads) on the CPU sample."""
+    from hopperrender_b200 import replay, synth
+    from oracle import OracleCalc
+    W, hdr = wl["W"], wl["hdr"]
+    o = OracleCalc(rows, W, 0, 0, 8, 6, 0.0, 255.0, rows, hdr)
+    o.setParams(searchRadius=SEARCH_RADIUS)
+    ring = [synth.make_frame(W, rows, t, hdr=hdr, noise=False) for t in range(4)]
+    for f in ring[:3]:
+        o.updateFrame(f)
+    out = np.zeros(o.outputFrameBytes, np.uint8)
+    state = {"i": 3, "blend": 0.0}
+
+    def step():
+        o.updateFrame(ring[state["i"] % len(ring)])
+        state["i"] += 1
+        o.calculateOpticalFlow()
+        n = replay.num_int_frames(state["blend"], wl["target"], replay.SOURCE_FRAME_TIME_23976)
+        for _ in range(n):
+            o.warpFrames(state["blend"], 2)
+            o.downloadFrame(out)
+            state["blend"] = replay.advance_blend(state["blend"], wl["target"], replay.SOURCE_FRAME_TIME_23976)
+        return n
+
+    return step
+
+
+def run_reference(args, wl, wl_name):
+    from oracle import num_threads
+    rank, world, _ = dist_env()
+    if rank != 0:
+        return
+    cores = num_threads()
+    per_step = max(1.0, min(8.0, 150.0 / (args.steps + args.warmup)))
+    rows = cpu_sample_rows(wl, per_step)
+    step = cpu_step_runner(wl, rows)
+    for _ in range(args.warmup):
+        step()
+    t0 = time.perf_counter()
+    frames = 0
+    for _ in range(args.steps):
+        frames += step()
+    dt = time.perf_counter() - t0
+    frac = rows / wl["H"]
+    value = frames * frac / dt
+    sample = (f"each step = one source frame (updateFrame + calculateOpticalFlow + N warpFrames + downloadFrame) on a full-width "
+              f"{wl['W']}x{rows} band of the workload frame ({frac:.4f} of the pixels); value = frames x {frac:.4f} / time "
+              f"(full-frame equivalent, linear in pixels)")
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8",
+        "data": "synthetic", "config": {"workload": f"{wl_name}: {wl['desc']}, R={SEARCH_RADIUS}", "search_radius": SEARCH_RADIUS},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def cpu_baseline(wl):
+    """Bounded CPU sample for the main line (rank 0, N=1): ~15 s of oracle work."""
+    from oracle import num_threads
+    rows = cpu_sample_rows(wl, 5.0)
+    step = cpu_step_runner(wl, rows)
+    step()
+    t0 = time.perf_counter()
+    frames = 0
+    for _ in range(2):
+        frames += step()
+    dt = time.perf_counter() - t0
+    frac = rows / wl["H"]
+    return {"value": frames * frac / dt, "unit": UNIT, "cores": num_threads(), "kind": "port",
+            "sample": f"2 source-frame steps on a full-width {wl['W']}x{rows} band ({frac:.4f} of the pixels), scaled linearly to the full frame"}
+
+
+# ------------------------------------------------------------------------------------------------------
+# the CUDA arm
+# ------------------------------------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=60)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="cfg3", choices=sorted(WORKLOADS))
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--radius", type=int, default=SEARCH_RADIUS)
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    wl = WORKLOADS[args.workload]
+    if args.impl == "reference":
+        run_reference(args, wl, args.workload)
+        return
+
+    import torch
+    import torch.distributed as dist
+
+    import hopperrender_b200 as hr
+    from hopperrender_b200 import replay, synth
+
+    rank, world, local = dist_env()
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device — hopperrender_b200 has no CPU fallback")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    W, H, hdr = wl["W"], wl["H"], wl["hdr"]
+    alg = algorithmic_bytes(wl)
+    stream = torch.cuda.Stream()
+    cls = hr.OpticalFlowCalcHDR if hdr else hr.OpticalFlowCalcSDR
+    calc = cls(H, W, 0, 0, 8, 6, 0.0, 255.0, wl["maxres"], device=local, stream=stream.cuda_stream)
+    calc.m_opticalFlowSearchRadius = args.radius
+
+    # synthetic frames: a ring of distinct frames, device-resident and pinned-host copies
+    RING = 6
+    dt_np = np.uint16 if hdr else np.uint8
+    host_frames = [synth.make_frame(W, H, t, synth.SEED_BASE + 2 + rank, hdr) for t in range(RING)]
+    tdt = torch.int16 if hdr else torch.uint8
+    pinned = [torch.from_numpy(f.view(np.int16) if hdr else f).pin_memory() for f in host_frames]
+    dev = [p.cuda(non_blocking=False) for p in pinned]
+    out_pinned = torch.empty(calc.outputFrameBytes // (2 if hdr else 1), dtype=tdt).pin_memory()
+    torch.cuda.synchronize()
+
+    total_steps = args.warmup + args.steps
+    sched = replay.output_schedule(2 * total_steps + 8, wl["target"], replay.SOURCE_FRAME_TIME_23976)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(ms):
+        if world > 1:
+            t = torch.tensor([ms], device="cuda", dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            return float(t.item())
+        return ms
+
+    def sum_over_ranks(v):
+        if world > 1:
+            t = torch.tensor([v], device="cuda", dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.SUM)
+            return float(t.item())
+        return float(v)
+
+    # ---- device-resident loop ---------------------------------------------------------------------
+    def step_device(i):
+        calc.updateFrameDevice(dev[i % RING])
+        calc.calculateOpticalFlowAsync()
+        for b in sched[i]:
+            calc.warpFrames(b, hr.BlendedFrame)
+        return len(sched[i])
+
+    def step_e2e(i):
+        calc.updateFrame(pinned[i % RING])
+        calc.calculateOpticalFlow()
+        for b in sched[i]:
+            calc.warpFrames(b, hr.BlendedFrame)
+            calc.downloadFrame(out_pinned)
+        return len(sched[i])
+
+    for i in range(3):  # prime the three input slots (m_frameCount >= 3, HopperRender.cpp:955)
+        calc.updateFrameDevice(dev[i % RING])
+    calc.synchronize()
+
+    idx = 0
+    for _ in range(args.warmup):
+        step_device(idx)
+        idx += 1
+    calc.synchronize()
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    launches0 = hr.kernel_launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    frames = 0
+    with torch.cuda.stream(stream):
+        e0.record(stream)
+        for _ in range(args.steps):
+            frames += step_device(idx)
+            idx += 1
+        e1.record(stream)
+    calc.synchronize()
+    barrier()
+    ms = max_over_ranks(e0.elapsed_time(e1))
+    launches = sum_over_ranks(hr.kernel_launch_count() - launches0)
+    clocks = sampler.stop() if rank == 0 else None
+    total_frames = sum_over_ranks(frames)
+    value = total_frames / (ms * 1e-3)
+
+    # ---- per-kernel breakdown (same loop, CUDA events around every kernel class on the handle's stream) ----
+    calc.setProfile(True)
+    calc.profileReset()
+    psteps = min(args.steps, 20)
+    pframes = 0
+    for _ in range(psteps):
+        pframes += step_device(idx)
+        idx += 1
+    prof = calc.profileRead()
+    calc.setProfile(False)
+
+    # ---- end-to-end loop (public blocking API, pinned host buffers) ------------------------------------
+    for _ in range(2):
+        step_e2e(idx)
+        idx += 1
+    barrier()
+    esteps = min(args.steps, 30)
+    eframes = 0
+    t0 = time.perf_counter()
+    with torch.cuda.stream(stream):
+        e0.record(stream)
+        for _ in range(esteps):
+            eframes += step_e2e(idx)
+            idx += 1
+        e1.record(stream)
+    calc.synchronize()
+    barrier()
+    e2e_wall_ms = (time.perf_counter() - t0) * 1e3
+    e2e_ms = max_over_ranks(max(e0.elapsed_time(e1), e2e_wall_ms))
+    e2e_value = sum_over_ranks(eframes) / (e2e_ms * 1e-3)
+    mean_out = eframes / esteps
+
+    if rank == 0:
+        pk, pk_kind = peaks()
+        hbm_peak = float(pk.get("hbm_gbs", 6650.0))
+        warp_ms = prof["ms_warp"] / max(prof["n_warp"], 1)
+        search_ms_per_step = prof["ms_search"] / psteps
+        warp_gbs = alg["warp"] / (warp_ms * 1e-3) / 1e9
+        sad_peak = None
+        try:
+            sad_peak = hr.microbench_sad_peak(local)
+        except Exception as e:  # noqa: BLE001
+            print(f"bench.py: SAD microbenchmark failed: {e}", file=sys.stderr)
+        absdiff_rate = 3.0 * args.radius * alg["L"] * alg["passes"] / (search_ms_per_step * 1e-3) / 1e9
+        step_kernel_ms = (prof["ms_ingest"] + prof["ms_search"] + prof["ms_blur"] + prof["ms_warp"]) / psteps
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8",
+            "data": "synthetic",
+            "config": {"workload": f"{args.workload}: {wl['desc']}, R={args.radius}", "search_radius": args.radius, "delta_scalar": 8,
+                       "neighbor_scalar": 6, "frame_output": "BlendedFrame", "streams_per_gpu": 1,
+                       "mean_outputs_per_source_frame": total_frames / world / args.steps,
+                       "realtime_factor_vs_144fps": value / world / 144.0,
+                       "l2": f"ring of {RING} distinct device frames; per-step working set ~{(3*alg['F'] + 2*4*W*H + 6*alg['L']*2 + alg['F'])/1e6:.0f} MB exceeds the 126 MB L2"},
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(calc.inputFrameBytes),
+                    "d2h_bytes_per_step": int(round(mean_out * calc.outputFrameBytes)), "steps": esteps},
+            "gpu_launches": int(launches),
+            "clocks": clocks,
+            "roofline": {"kernel": "warpFrameKernel (dominant HBM-bound kernel, %d launches/step)" % round(mean_out), "bound": "hbm",
+                         "achieved": warp_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": warp_gbs / hbm_peak, "traffic": None,
+                         "peak_source": f"{pk_kind} (MEASURED_PEAKS.json hbm_gbs)", "algorithmic_bytes_per_launch": alg["warp"],
+                         "avg_launch_ms": warp_ms},
+            "roofline_search": {"kernel": "sadPassKernel ladder (dominant by time, integer-ALU bound)", "bound": "int_alu",
+                                "achieved": absdiff_rate, "peak": sad_peak, "unit": "G byte-absdiff/s",
+                                "frac": (absdiff_rate / sad_peak) if sad_peak else None,
+                                "peak_source": "hrb_microbench_sad_peak: VABSDIFF4.U8.ACC issue rate measured in this run",
+                                "algorithmic_absdiff_per_step": 3 * args.radius * alg["L"] * alg["passes"], "ms_per_step": search_ms_per_step},
+            "breakdown_ms_per_step": {"ingest": prof["ms_ingest"] / psteps, "search": search_ms_per_step, "blur": prof["ms_blur"] / psteps,
+                                      "warp": prof["ms_warp"] / psteps, "kernels_total": step_kernel_ms},
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            try:
+                line["cpu_baseline"] = cpu_baseline(wl)
+            except Exception as e:  # noqa: BLE001
+                line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": 0, "kind": "port", "sample": f"failed: {e}"}
+        print(json.dumps(line), flush=True)
+    calc.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,794 @@
+// hrb_api.cu — handle management, the per-frame host schedule and the C ABI (include/hrb.h).
+// The schedule restates HopperRender/opticalFlowCalcSDR.cpp / opticalFlowCalcHDR.cpp on one CUDA stream.
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <new>
+
+#include "hrb_internal.cuh"
+
+namespace hrb {
+
+static thread_local std::string t_lastError;
+unsigned long long g_launchCount = 0;
+
+void setLastError(const char* fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    t_lastError = buf;
+    // the reference also reports on stderr (opticalFlowCalc.h:19-20)
+    fputs(buf, stderr);
+    fputc('\n', stderr);
+}
+
+// ---- profiling -----------------------------------------------------------------------------------
+static cudaEvent_t profEvent(hrb_ofc* h) {
+    if (!h->prof.pool.empty()) {
+        cudaEvent_t e = h->prof.pool.back();
+        h->prof.pool.pop_back();
+        return e;
+    }
+    cudaEvent_t e = nullptr;
+    cudaEventCreate(&e);
+    return e;
+}
+
+void profBegin(hrb_ofc* h, int cls) {
+    if (!h->prof.on) return;
+    Profile::Pending p;
+    p.a = profEvent(h);
+    p.b = nullptr;
+    p.cls = cls;
+    cudaEventRecord(p.a, h->stream);
+    h->prof.pending.push_back(p);
+}
+
+void profEnd(hrb_ofc* h, int cls, unsigned launches) {
+    h->prof.n[cls] += launches;
+    if (!h->prof.on || h->prof.pending.empty()) return;
+    Profile::Pending& p = h->prof.pending.back();
+    p.b = profEvent(h);
+    cudaEventRecord(p.b, h->stream);
+}
+
+static int profResolve(hrb_ofc* h) {
+    if (h->prof.pending.empty()) return HRB_OK;
+    HRB_CUDA(cudaStreamSynchronize(h->stream));
+    for (auto& p : h->prof.pending) {
+        if (p.a && p.b) {
+            float ms = 0;
+            if (cudaEventElapsedTime(&ms, p.a, p.b) == cudaSuccess) h->prof.ms[p.cls] += ms;
+        }
+        if (p.a) h->prof.pool.push_back(p.a);
+        if (p.b) h->prof.pool.push_back(p.b);
+    }
+    h->prof.pending.clear();
+    return HRB_OK;
+}
+
+// ---- taps ----------------------------------------------------------------------------------------
+static void freeTaps(hrb_ofc* h) {
+    for (auto& t : h->taps) {
+        cudaFree(t.sums);
+        cudaFree(t.layer);
+        cudaFree(t.offX);
+        cudaFree(t.offY);
+    }
+    h->taps.clear();
+}
+
+static int ilog2(int v) {
+    int l = 0;
+    while ((1 << (l + 1)) <= v) ++l;
+    return l;
+}
+
+// First window size and iteration count — opticalFlowCalcSDR.cpp:49-65 (NUM_ITERATIONS == 0)
+static void ladder(int lw, int lh, int* ws0, int* iterations) {
+    int windowSize = 1;
+    int maxDim = lw > lh ? lw : lh;
+    if (maxDim && !(maxDim & (maxDim - 1))) {
+        windowSize = maxDim;
+    } else {
+        while (maxDim & (maxDim - 1)) maxDim &= (maxDim - 1);
+        windowSize = maxDim << 1;
+    }
+    windowSize /= 2;
+    *ws0 = windowSize;
+    *iterations = ilog2(windowSize);
+}
+
+// The stats block at the end of calculateOpticalFlow — opticalFlowCalcSDR.cpp:119-138
+static int resolveRecord(hrb_ofc* h, hrb_ofc::FlowRecord& r) {
+    if (!r.pending) return HRB_OK;
+    HRB_CUDA(cudaEventSynchronize(r.end));
+    r.pending = false;
+    // m_totalFrameDelta — opticalFlowCalcSDR.cpp:92-93 (divisor 10) / opticalFlowCalcHDR.cpp:92-93 (divisor 6)
+    h->totalFrameDelta = *r.rawDeltaHost;
+    h->totalFrameDelta /= (unsigned)(h->flowHeight * h->flowWidth * (h->hdr ? 6 : 10));
+    float ms = 0;
+    HRB_CUDA(cudaEventElapsedTime(&ms, r.start, r.end));
+    h->ofcCalcTime = (double)ms / 1e3;
+    if (h->ofcCalcCount >= 240) {  // CALC_TIME_INTERVAL, config.h:17
+        h->ofcAvgCalcTime = h->ofcCalcTimeSum / h->ofcCalcCount;
+        h->ofcCalcCount = 0;
+        h->ofcCalcTimeSum = 0.0;
+        h->ofcPeakCalcTime = h->ofcCalcTime;
+    }
+    h->ofcCalcCount++;
+    h->ofcCalcTimeSum += h->ofcCalcTime;
+    if (h->ofcCalcTime > h->ofcPeakCalcTime) h->ofcPeakCalcTime = h->ofcCalcTime;
+    return HRB_OK;
+}
+
+// resolve every flow in flight, oldest first
+static int resolveFlow(hrb_ofc* h) {
+    for (int i = 1; i <= hrb_ofc::kFlowRecords; ++i) {
+        const int rc = resolveRecord(h, h->flowRec[(h->curRec + i) % hrb_ofc::kFlowRecords]);
+        if (rc) return rc;
+    }
+    return HRB_OK;
+}
+
+static int enqueueFlow(hrb_ofc* h) {
+    HRB_CUDA(cudaSetDevice(h->device));
+    hrb_ofc::FlowRecord& rec = h->flowRec[h->curRec];
+    if (rec.pending) {  // a second calculate on the same upload: its end event is about to be re-recorded
+        const int rc = resolveFlow(h);
+        if (rc) return rc;
+    }
+    const int R = h->searchRadius;  // m_lowGrid8x8xL[2] = m_opticalFlowSearchRadius, opticalFlowCalcSDR.cpp:46
+    if (R < 2 || R > 16) {
+        setLastError("[hopperrender_b200] search radius %d outside 2..16", R);
+        return HRB_ERR_INVALID_ARG;
+    }
+    if (h->deltaScalar < 0 || h->deltaScalar > 31 || h->neighborBiasScalar < 0 || h->neighborBiasScalar > 31) {
+        setLastError("[hopperrender_b200] delta/neighbor scalar outside 0..31");
+        return HRB_ERR_INVALID_ARG;
+    }
+    const int lw = h->flowWidth, lh = h->flowHeight;
+    int ws0, iterations;
+    ladder(lw, lh, &ws0, &iterations);
+    if (!rec.startValid) {  // calculate without a preceding updateFrame: time from here
+        HRB_CUDA(cudaEventRecord(rec.start, h->stream));
+        rec.startValid = true;
+    }
+    if (h->tapMode) freeTaps(h);
+
+    SearchArgs a;
+    memset(&a, 0, sizeof(a));
+    a.plane1 = h->searchPlane[1];  // frame1 = m_inputFrameArray[1], opticalFlowCalcSDR.cpp:79
+    a.plane2 = h->searchPlane[2];  // frame2 = m_inputFrameArray[2], opticalFlowCalcSDR.cpp:80
+    a.pitch = h->planePitch;
+    a.W = h->frameWidth;
+    a.H = h->frameHeight;
+    a.lw = lw;
+    a.lh = lh;
+    a.rs = h->resScalar;
+    a.deltaScalar = h->deltaScalar;
+    a.neighborBiasScalar = h->neighborBiasScalar;
+    a.winSums = h->winSums;
+
+    int prevNWx = 0, prevNWy = 0;
+    for (int iter = 0; iter < iterations; ++iter) {
+        const int ws = ws0 >> iter;
+        const int par = iter & 1;
+        a.ws = ws;
+        a.wsLog2 = ilog2(ws);
+        a.iteration = iter;
+        a.nWx = (lw + ws - 1) / ws;
+        a.nWy = (lh + ws - 1) / ws;
+        a.prevNWx = prevNWx;
+        a.prevX = iter ? h->levelOffsets[par ^ 1][0] : nullptr;
+        a.prevY = iter ? h->levelOffsets[par ^ 1][1] : nullptr;
+        a.curX = h->levelOffsets[par][0];
+        a.curY = h->levelOffsets[par][1];
+        for (int step = 0; step < 2; ++step) {
+            a.rawDelta = (iter == 0 && step == 0) ? h->rawDeltaDev : nullptr;
+            a.tapSums = nullptr;
+            a.tapLayer = nullptr;
+            if (h->tapMode) {
+                PassTapDev t;
+                t.g.windowSize = ws;
+                t.g.wsLog2 = a.wsLog2;
+                t.g.iteration = iter;
+                t.g.step = step;
+                t.g.nWx = a.nWx;
+                t.g.nWy = a.nWy;
+                t.g.prevNWx = prevNWx;
+                t.g.prevNWy = prevNWy;
+                const size_t nW = (size_t)a.nWx * a.nWy;
+                HRB_CUDA(cudaMalloc(&t.sums, nW * R * sizeof(uint32_t)));
+                HRB_CUDA(cudaMalloc(&t.layer, nW));
+                HRB_CUDA(cudaMalloc(&t.offX, nW * sizeof(int16_t)));
+                HRB_CUDA(cudaMalloc(&t.offY, nW * sizeof(int16_t)));
+                HRB_CUDA(cudaMemsetAsync(t.sums, 0, nW * R * sizeof(uint32_t), h->stream));
+                a.tapSums = t.sums;
+                a.tapLayer = t.layer;
+                h->taps.push_back(t);
+            }
+            const int rc = launchSearchPass(h, a, R, step);
+            if (rc) return rc;
+            if (h->tapMode) {
+                PassTapDev& t = h->taps.back();
+                const size_t nW = (size_t)a.nWx * a.nWy;
+                HRB_CUDA(cudaMemcpyAsync(t.offX, a.curX, nW * sizeof(int16_t), cudaMemcpyDeviceToDevice, h->stream));
+                t.wsX = ws;
+                t.nWxX = a.nWx;
+                t.nWyX = a.nWy;
+                if (step == 1) {
+                    HRB_CUDA(cudaMemcpyAsync(t.offY, a.curY, nW * sizeof(int16_t), cudaMemcpyDeviceToDevice, h->stream));
+                    t.wsY = ws;
+                    t.nWxY = a.nWx;
+                    t.nWyY = a.nWy;
+                } else if (iter > 0) {
+                    HRB_CUDA(cudaMemcpyAsync(t.offY, a.prevY, (size_t)prevNWx * prevNWy * sizeof(int16_t), cudaMemcpyDeviceToDevice, h->stream));
+                    t.wsY = ws * 2;
+                    t.nWxY = prevNWx;
+                    t.nWyY = prevNWy;
+                } else {
+                    t.wsY = 0;  // all zero
+                }
+            }
+        }
+        prevNWx = a.nWx;
+        prevNWy = a.nWy;
+        h->lastIterParity = par;
+        h->lastNWx = a.nWx;
+        h->lastNWy = a.nWy;
+        h->lastWs = ws;
+    }
+    h->haveFlowLevels = true;
+
+    // blur into m_blurredOffsetArray[0], then swap (opticalFlowCalcSDR.cpp:113-123)
+    {
+        const int rc = launchBlurFlow(h, h->levelOffsets[h->lastIterParity][0], h->levelOffsets[h->lastIterParity][1], h->lastNWx, ilog2(h->lastWs),
+                                      h->blurredOffsetArray[0]);
+        if (rc) return rc;
+    }
+    HRB_CUDA(cudaMemcpyAsync(rec.rawDeltaHost, h->rawDeltaDev, sizeof(uint32_t), cudaMemcpyDeviceToHost, h->stream));
+    HRB_CUDA(cudaEventRecord(rec.end, h->stream));
+    int16_t* t0 = h->blurredOffsetArray[0];
+    h->blurredOffsetArray[0] = h->blurredOffsetArray[1];
+    h->blurredOffsetArray[1] = t0;
+    rec.pending = true;
+    return HRB_OK;
+}
+
+static int finishUpdate(hrb_ofc* h) {
+    // rotate: [0] <- [1] <- [2] <- new (opticalFlowCalcSDR.cpp:22-26)
+    uint8_t* f0 = h->inputFrameArray[0];
+    h->inputFrameArray[0] = h->inputFrameArray[1];
+    h->inputFrameArray[1] = h->inputFrameArray[2];
+    h->inputFrameArray[2] = f0;
+    uint32_t* p0 = h->searchPlane[0];
+    h->searchPlane[0] = h->searchPlane[1];
+    h->searchPlane[1] = h->searchPlane[2];
+    h->searchPlane[2] = p0;
+    h->frameCount++;
+    return launchPackFrame(h, 2);
+}
+
+static int beginUpdate(hrb_ofc* h) {
+    HRB_CUDA(cudaSetDevice(h->device));
+    h->curRec = (h->curRec + 1) % hrb_ofc::kFlowRecords;
+    hrb_ofc::FlowRecord& rec = h->flowRec[h->curRec];
+    if (rec.pending) {  // the ring is full: wait for the oldest flow before reusing its events
+        const int rc = resolveRecord(h, rec);
+        if (rc) return rc;
+    }
+    HRB_CUDA(cudaEventRecord(rec.start, h->stream));  // m_ofcStartedEvent, opticalFlowCalcSDR.cpp:20
+    rec.startValid = true;
+    return HRB_OK;
+}
+
+}  // namespace hrb
+
+using namespace hrb;
+
+#define HRB_REQUIRE(cond, msg)                                       \
+    do {                                                             \
+        if (!(cond)) {                                               \
+            setLastError("[hopperrender_b200] %s: %s", __func__, msg); \
+            return HRB_ERR_INVALID_ARG;                              \
+        }                                                            \
+    } while (0)
+
+extern "C" {
+
+int hrb_ofc_create(hrb_ofc** out, const hrb_ofc_desc* d) {
+    HRB_REQUIRE(out && d, "null argument");
+    *out = nullptr;
+    HRB_REQUIRE(d->frame_width >= 16 && d->frame_height >= 16, "frame must be at least 16x16");
+    HRB_REQUIRE((d->frame_width % 2) == 0 && (d->frame_height % 2) == 0, "NV12/P010 frame dimensions must be even");
+    HRB_REQUIRE(d->max_calc_res >= 1, "max_calc_res must be positive");
+    int nDev = 0;
+    if (cudaGetDeviceCount(&nDev) != cudaSuccess || nDev == 0) {
+        setLastError("[hopperrender_b200] no CUDA device (this library has no CPU fallback)");
+        return HRB_ERR_NO_DEVICE;
+    }
+    HRB_REQUIRE(d->device_ordinal >= 0 && d->device_ordinal < nDev, "device_ordinal out of range");
+    HRB_CUDA(cudaSetDevice(d->device_ordinal));
+
+    hrb_ofc* h = new (std::nothrow) hrb_ofc();
+    HRB_REQUIRE(h, "out of host memory");
+    // opticalFlowCalcSDR.cpp:208-232
+    h->frameWidth = d->frame_width;
+    h->frameHeight = d->frame_height;
+    h->inputStride = d->input_stride > 0 ? d->input_stride : d->frame_width;
+    h->outputStride = d->output_stride > 0 ? d->output_stride : d->frame_width;
+    h->outputBlackLevel = d->black_level;
+    h->outputWhiteLevel = d->white_level;
+    h->hdr = d->is_hdr ? 1 : 0;
+    h->bpp = h->hdr ? 2 : 1;
+    h->searchRadius = 5;  // MIN_SEARCH_RADIUS, config.h:8
+    h->resScalar = 0;
+    while ((d->frame_height >> h->resScalar) > d->max_calc_res) h->resScalar++;
+    h->flowWidth = (int)std::ceil(h->frameWidth / std::pow(2, h->resScalar));
+    h->flowHeight = (int)std::ceil(h->frameHeight / std::pow(2, h->resScalar));
+    h->ofcCalcTime = h->ofcAvgCalcTime = h->ofcPeakCalcTime = 0.0;
+    h->ofcCalcCount = 0;
+    h->ofcCalcTimeSum = 0.0;
+    h->warpCalcTime = 0.0;
+    h->deltaScalar = d->delta_scalar;
+    h->neighborBiasScalar = d->neighbor_scalar;
+    h->totalFrameDelta = 0;
+    h->frameCount = 0;
+    h->device = d->device_ordinal;
+    h->stream = nullptr;
+    h->ownStream = false;
+    h->warpStartedValid = false;
+    h->curRec = 0;
+    for (auto& r : h->flowRec) {
+        r.start = r.end = nullptr;
+        r.rawDeltaHost = nullptr;
+        r.startValid = r.pending = false;
+    }
+    h->haveFlowLevels = false;
+    h->tapMode = false;
+    h->lastIterParity = 0;
+    h->lastNWx = h->lastNWy = h->lastWs = 0;
+    for (int i = 0; i < 3; ++i) {
+        h->inputFrameArray[i] = nullptr;
+        h->searchPlane[i] = nullptr;
+    }
+    h->outputFrameArray = nullptr;
+    h->levelOffsets[0][0] = h->levelOffsets[0][1] = h->levelOffsets[1][0] = h->levelOffsets[1][1] = nullptr;
+    h->winSums = nullptr;
+    h->offsetArrayScratch = nullptr;
+    h->blurredOffsetArray[0] = h->blurredOffsetArray[1] = nullptr;
+    h->rawDeltaDev = nullptr;
+    h->warpStartedEvent = h->warpEndEvent = h->uploadDoneEvent = nullptr;
+
+    auto fail = [&](int rc) {
+        hrb_ofc_destroy(h);
+        return rc;
+    };
+    if (h->inputStride < h->frameWidth || h->outputStride < h->frameWidth) {
+        setLastError("[hopperrender_b200] hrb_ofc_create: stride smaller than the frame width");
+        return fail(HRB_ERR_INVALID_ARG);
+    }
+    if (h->flowWidth < 4 || h->flowHeight < 4) {
+        setLastError("[hopperrender_b200] hrb_ofc_create: flow resolution %dx%d is below 4x4 (raise max_calc_res)", h->flowWidth, h->flowHeight);
+        return fail(HRB_ERR_INVALID_ARG);
+    }
+
+    const size_t lw = h->flowWidth, lh = h->flowHeight;
+    h->inFrameBytes = ((size_t)h->frameHeight * h->inputStride + (size_t)(h->frameHeight / 2) * h->inputStride) * h->bpp;
+    h->outFrameBytes = ((size_t)h->frameHeight * h->outputStride + (size_t)(h->frameHeight / 2) * h->outputStride) * h->bpp;
+    h->planePitch = (h->frameWidth + 31) & ~31;
+    const size_t planeBytes = (size_t)h->planePitch * h->frameHeight * sizeof(uint32_t);
+    h->levelCapacity = ((lw + 1) / 2) * ((lh + 1) / 2);
+    const size_t winSumEntries = ((lw + 63) / 64) * ((lh + 63) / 64) * 16 + 16;
+    const size_t need = 3 * (h->inFrameBytes + planeBytes) + h->outFrameBytes + 4 * h->levelCapacity * 2 + winSumEntries * 4 + 3 * 2 * lw * lh * 2;
+
+    // replaces detectDevices' memory check (opticalFlowCalc.cpp:48-51,86-96)
+    size_t freeB = 0, totalB = 0;
+    if (cudaMemGetInfo(&freeB, &totalB) != cudaSuccess) {
+        setLastError("[hopperrender_b200] device %d is not usable: %s", h->device, cudaGetErrorString(cudaGetLastError()));
+        return fail(HRB_ERR_CUDA);
+    }
+    if (freeB < need + (64u << 20)) {
+        setLastError("[hopperrender_b200] device %d has %zu MiB free, %zu MiB needed", h->device, freeB >> 20, need >> 20);
+        return fail(HRB_ERR_NO_DEVICE);
+    }
+
+#define HRB_TRY(call)                                                                                                      \
+    do {                                                                                                                   \
+        cudaError_t _e = (call);                                                                                           \
+        if (_e != cudaSuccess) {                                                                                           \
+            setLastError("[hopperrender_b200] CUDA error %d (%s) in hrb_ofc_create at %s:%d", (int)_e, cudaGetErrorString(_e), \
+                         __FILE__, __LINE__);                                                                              \
+            return fail(HRB_ERR_CUDA);                                                                                     \
+        }                                                                                                                  \
+    } while (0)
+
+    if (d->cuda_stream) {
+        h->stream = (cudaStream_t)d->cuda_stream;
+    } else {
+        HRB_TRY(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+        h->ownStream = true;
+    }
+    for (auto& r : h->flowRec) {
+        HRB_TRY(cudaEventCreate(&r.start));
+        HRB_TRY(cudaEventCreate(&r.end));
+        HRB_TRY(cudaMallocHost(&r.rawDeltaHost, sizeof(uint32_t)));
+        *r.rawDeltaHost = 0;
+    }
+    HRB_TRY(cudaEventCreate(&h->warpStartedEvent));
+    HRB_TRY(cudaEventCreate(&h->warpEndEvent));
+    HRB_TRY(cudaEventCreateWithFlags(&h->uploadDoneEvent, cudaEventDisableTiming));
+    for (int i = 0; i < 3; ++i) {
+        HRB_TRY(cudaMalloc(&h->inputFrameArray[i], h->inFrameBytes));
+        HRB_TRY(cudaMemsetAsync(h->inputFrameArray[i], 0, h->inFrameBytes, h->stream));
+        HRB_TRY(cudaMalloc(&h->searchPlane[i], planeBytes));
+        HRB_TRY(cudaMemsetAsync(h->searchPlane[i], 0, planeBytes, h->stream));
+    }
+    HRB_TRY(cudaMalloc(&h->outputFrameArray, h->outFrameBytes));
+    HRB_TRY(cudaMemsetAsync(h->outputFrameArray, 0, h->outFrameBytes, h->stream));
+    for (int p = 0; p < 2; ++p)
+        for (int ax = 0; ax < 2; ++ax) {
+            HRB_TRY(cudaMalloc(&h->levelOffsets[p][ax], h->levelCapacity * sizeof(int16_t)));
+            HRB_TRY(cudaMemsetAsync(h->levelOffsets[p][ax], 0, h->levelCapacity * sizeof(int16_t), h->stream));
+        }
+    HRB_TRY(cudaMalloc(&h->winSums, winSumEntries * sizeof(uint32_t)));
+    HRB_TRY(cudaMalloc(&h->offsetArrayScratch, 2 * lw * lh * sizeof(int16_t)));
+    for (int i = 0; i < 2; ++i) {
+        HRB_TRY(cudaMalloc(&h->blurredOffsetArray[i], 2 * lw * lh * sizeof(int16_t)));
+        HRB_TRY(cudaMemsetAsync(h->blurredOffsetArray[i], 0, 2 * lw * lh * sizeof(int16_t), h->stream));
+    }
+    HRB_TRY(cudaMalloc(&h->rawDeltaDev, sizeof(uint32_t)));
+    HRB_TRY(cudaMemsetAsync(h->rawDeltaDev, 0, sizeof(uint32_t), h->stream));
+    HRB_TRY(cudaStreamSynchronize(h->stream));
+#undef HRB_TRY
+    *out = h;
+    return HRB_OK;
+}
+
+void hrb_ofc_destroy(hrb_ofc* h) {
+    if (!h) return;
+    cudaSetDevice(h->device);
+    if (h->stream) cudaStreamSynchronize(h->stream);  // clFinish, opticalFlowCalcSDR.cpp:186
+    freeTaps(h);
+    for (auto& p : h->prof.pending) {
+        if (p.a) cudaEventDestroy(p.a);
+        if (p.b) cudaEventDestroy(p.b);
+    }
+    for (auto e : h->prof.pool) cudaEventDestroy(e);
+    for (int i = 0; i < 3; ++i) {
+        cudaFree(h->inputFrameArray[i]);
+        cudaFree(h->searchPlane[i]);
+    }
+    cudaFree(h->outputFrameArray);
+    for (int p = 0; p < 2; ++p)
+        for (int ax = 0; ax < 2; ++ax) cudaFree(h->levelOffsets[p][ax]);
+    cudaFree(h->winSums);
+    cudaFree(h->offsetArrayScratch);
+    cudaFree(h->blurredOffsetArray[0]);
+    cudaFree(h->blurredOffsetArray[1]);
+    cudaFree(h->rawDeltaDev);
+    for (auto& r : h->flowRec) {
+        if (r.rawDeltaHost) cudaFreeHost(r.rawDeltaHost);
+        if (r.start) cudaEventDestroy(r.start);
+        if (r.end) cudaEventDestroy(r.end);
+    }
+    if (h->warpStartedEvent) cudaEventDestroy(h->warpStartedEvent);
+    if (h->warpEndEvent) cudaEventDestroy(h->warpEndEvent);
+    if (h->uploadDoneEvent) cudaEventDestroy(h->uploadDoneEvent);
+    if (h->ownStream && h->stream) cudaStreamDestroy(h->stream);
+    delete h;
+}
+
+int hrb_ofc_update_frame(hrb_ofc* h, const uint8_t* input_planes) {
+    HRB_REQUIRE(h && input_planes, "null argument");
+    int rc = beginUpdate(h);
+    if (rc) return rc;
+    // blocking write into m_inputFrameArray[0] (opticalFlowCalcSDR.cpp:20)
+    HRB_CUDA(cudaMemcpyAsync(h->inputFrameArray[0], input_planes, h->inFrameBytes, cudaMemcpyHostToDevice, h->stream));
+    HRB_CUDA(cudaEventRecord(h->uploadDoneEvent, h->stream));
+    rc = finishUpdate(h);
+    if (rc) return rc;
+    HRB_CUDA(cudaEventSynchronize(h->uploadDoneEvent));  // the caller's buffer is free again; packing continues asynchronously
+    return HRB_OK;
+}
+
+int hrb_ofc_update_frame_device(hrb_ofc* h, const void* device_planes) {
+    HRB_REQUIRE(h && device_planes, "null argument");
+    int rc = beginUpdate(h);
+    if (rc) return rc;
+    HRB_CUDA(cudaMemcpyAsync(h->inputFrameArray[0], device_planes, h->inFrameBytes, cudaMemcpyDeviceToDevice, h->stream));
+    return finishUpdate(h);
+}
+
+int hrb_ofc_calculate_optical_flow_async(hrb_ofc* h) {
+    HRB_REQUIRE(h, "null handle");
+    return enqueueFlow(h);
+}
+
+int hrb_ofc_calculate_optical_flow(hrb_ofc* h) {
+    HRB_REQUIRE(h, "null handle");
+    const int rc = enqueueFlow(h);
+    if (rc) return rc;
+    return resolveFlow(h);
+}
+
+int hrb_ofc_warp_frames(hrb_ofc* h, float blending_scalar, int frame_output_mode) {
+    HRB_REQUIRE(h, "null handle");
+    if (blending_scalar > 1.0f) {  // opticalFlowCalcSDR.cpp:143-146
+        setLastError("[HopperRender] Error in function warpFrames: Blending scalar is greater than 1.0");
+        return HRB_ERR_BLEND_RANGE;
+    }
+    HRB_REQUIRE(frame_output_mode >= 0 && frame_output_mode <= 6, "frame_output_mode outside 0..6");
+    HRB_CUDA(cudaSetDevice(h->device));
+    HRB_CUDA(cudaEventRecord(h->warpStartedEvent, h->stream));  // m_warpStartedEvent, opticalFlowCalcSDR.cpp:164
+    h->warpStartedValid = true;
+    return launchWarpFrame(h, blending_scalar, frame_output_mode);
+}
+
+int hrb_ofc_copy_frame(hrb_ofc* h) {
+    HRB_REQUIRE(h, "null handle");
+    HRB_CUDA(cudaSetDevice(h->device));
+    const int frameIndex = h->frameCount >= 3 ? 0 : h->frameCount >= 2 ? 1 : 2;  // opticalFlowCalcSDR.cpp:173
+    HRB_CUDA(cudaEventRecord(h->warpStartedEvent, h->stream));
+    h->warpStartedValid = true;
+    return launchCopyFrame(h, frameIndex);
+}
+
+int hrb_ofc_download_frame(hrb_ofc* h, uint8_t* output_planes) {
+    HRB_REQUIRE(h && output_planes, "null argument");
+    HRB_CUDA(cudaSetDevice(h->device));
+    HRB_CUDA(cudaMemcpyAsync(output_planes, h->outputFrameArray, h->outFrameBytes, cudaMemcpyDeviceToHost, h->stream));
+    HRB_CUDA(cudaEventRecord(h->warpEndEvent, h->stream));
+    HRB_CUDA(cudaEventSynchronize(h->warpEndEvent));
+    if (h->warpStartedValid) {  // opticalFlowCalcSDR.cpp:36-41
+        float ms = 0;
+        HRB_CUDA(cudaEventElapsedTime(&ms, h->warpStartedEvent, h->warpEndEvent));
+        h->warpCalcTime = (double)ms / 1e3;
+    }
+    return HRB_OK;
+}
+
+int hrb_ofc_download_frame_async(hrb_ofc* h, uint8_t* pinned_output_planes) {
+    HRB_REQUIRE(h && pinned_output_planes, "null argument");
+    HRB_CUDA(cudaSetDevice(h->device));
+    HRB_CUDA(cudaMemcpyAsync(pinned_output_planes, h->outputFrameArray, h->outFrameBytes, cudaMemcpyDeviceToHost, h->stream));
+    return HRB_OK;
+}
+
+int hrb_ofc_synchronize(hrb_ofc* h) {
+    HRB_REQUIRE(h, "null handle");
+    HRB_CUDA(cudaSetDevice(h->device));
+    HRB_CUDA(cudaStreamSynchronize(h->stream));
+    return resolveFlow(h);
+}
+
+int hrb_ofc_stream(hrb_ofc* h, void** out) {
+    HRB_REQUIRE(h && out, "null argument");
+    *out = (void*)h->stream;
+    return HRB_OK;
+}
+
+int hrb_ofc_output_device_ptr(hrb_ofc* h, void** out) {
+    HRB_REQUIRE(h && out, "null argument");
+    *out = h->outputFrameArray;
+    return HRB_OK;
+}
+
+int hrb_host_register(void* ptr, size_t bytes) {
+    HRB_REQUIRE(ptr && bytes, "null argument");
+    HRB_CUDA(cudaHostRegister(ptr, bytes, cudaHostRegisterPortable));
+    return HRB_OK;
+}
+int hrb_host_unregister(void* ptr) {
+    HRB_REQUIRE(ptr, "null argument");
+    HRB_CUDA(cudaHostUnregister(ptr));
+    return HRB_OK;
+}
+int hrb_host_alloc(void** out, size_t bytes) {
+    HRB_REQUIRE(out && bytes, "null argument");
+    HRB_CUDA(cudaHostAlloc(out, bytes, cudaHostAllocPortable));
+    return HRB_OK;
+}
+int hrb_host_free(void* ptr) {
+    HRB_REQUIRE(ptr, "null argument");
+    HRB_CUDA(cudaFreeHost(ptr));
+    return HRB_OK;
+}
+
+int hrb_ofc_get_state(hrb_ofc* h, hrb_ofc_state* s) {
+    HRB_REQUIRE(h && s, "null argument");
+    const int rc = resolveFlow(h);
+    if (rc) return rc;
+    s->frame_width = h->frameWidth;
+    s->frame_height = h->frameHeight;
+    s->input_stride = h->inputStride;
+    s->output_stride = h->outputStride;
+    s->output_black_level = h->outputBlackLevel;
+    s->output_white_level = h->outputWhiteLevel;
+    s->res_scalar = h->resScalar;
+    s->flow_width = h->flowWidth;
+    s->flow_height = h->flowHeight;
+    s->search_radius = h->searchRadius;
+    s->ofc_calc_time = h->ofcCalcTime;
+    s->ofc_avg_calc_time = h->ofcAvgCalcTime;
+    s->ofc_peak_calc_time = h->ofcPeakCalcTime;
+    s->ofc_calc_count = h->ofcCalcCount;
+    s->ofc_calc_time_sum = h->ofcCalcTimeSum;
+    s->warp_calc_time = h->warpCalcTime;
+    s->delta_scalar = h->deltaScalar;
+    s->neighbor_bias_scalar = h->neighborBiasScalar;
+    s->total_frame_delta = h->totalFrameDelta;
+    s->frame_count = h->frameCount;
+    return HRB_OK;
+}
+
+int hrb_ofc_set_params(hrb_ofc* h, const hrb_ofc_params* p) {
+    HRB_REQUIRE(h && p, "null argument");
+    h->searchRadius = p->search_radius;
+    h->deltaScalar = p->delta_scalar;
+    h->neighborBiasScalar = p->neighbor_bias_scalar;
+    h->outputBlackLevel = p->black_level;
+    h->outputWhiteLevel = p->white_level;
+    return HRB_OK;
+}
+
+int hrb_ofc_set_frame_count(hrb_ofc* h, unsigned int n) {
+    HRB_REQUIRE(h, "null handle");
+    h->frameCount = n;
+    return HRB_OK;
+}
+
+int hrb_ofc_reset(hrb_ofc* h) { return hrb_ofc_set_frame_count(h, 0); }
+
+// ---- taps ----------------------------------------------------------------------------------------
+int hrb_ofc_set_tap_mode(hrb_ofc* h, int on) {
+    HRB_REQUIRE(h, "null handle");
+    HRB_CUDA(cudaSetDevice(h->device));
+    HRB_CUDA(cudaStreamSynchronize(h->stream));
+    h->tapMode = on != 0;
+    if (!h->tapMode) freeTaps(h);
+    return HRB_OK;
+}
+
+int hrb_ofc_num_passes(hrb_ofc* h, int* out) {
+    HRB_REQUIRE(h && out, "null argument");
+    *out = (int)h->taps.size();
+    return HRB_OK;
+}
+
+int hrb_ofc_pass_info(hrb_ofc* h, int pass, int* window_size, int* iteration, int* step, int* windows_x, int* windows_y) {
+    HRB_REQUIRE(h, "null handle");
+    HRB_REQUIRE(pass >= 0 && pass < (int)h->taps.size(), "pass out of range (is tap mode on?)");
+    const PassGeom& g = h->taps[pass].g;
+    if (window_size) *window_size = g.windowSize;
+    if (iteration) *iteration = g.iteration;
+    if (step) *step = g.step;
+    if (windows_x) *windows_x = g.nWx;
+    if (windows_y) *windows_y = g.nWy;
+    return HRB_OK;
+}
+
+int hrb_ofc_read_pass_tap(hrb_ofc* h, int pass, int which, void* dst, size_t bytes) {
+    HRB_REQUIRE(h && dst, "null argument");
+    if (pass < 0 || pass >= (int)h->taps.size()) {
+        setLastError("[hopperrender_b200] hrb_ofc_read_pass_tap: no such pass (tap mode must be on before calculate)");
+        return HRB_ERR_STATE;
+    }
+    HRB_CUDA(cudaSetDevice(h->device));
+    const PassTapDev& t = h->taps[pass];
+    const size_t nW = (size_t)t.g.nWx * t.g.nWy;
+    const size_t lwlh = (size_t)h->flowWidth * h->flowHeight;
+    if (which == HRB_TAP_WINDOW_SUMS) {
+        HRB_REQUIRE(bytes <= nW * 16 * sizeof(uint32_t) && bytes % (nW * sizeof(uint32_t)) == 0, "size must be R*windows*4");
+        HRB_CUDA(cudaMemcpyAsync(dst, t.sums, bytes, cudaMemcpyDeviceToHost, h->stream));
+    } else if (which == HRB_TAP_WINDOW_LAYER) {
+        HRB_REQUIRE(bytes == nW, "size must be windows");
+        HRB_CUDA(cudaMemcpyAsync(dst, t.layer, bytes, cudaMemcpyDeviceToHost, h->stream));
+    } else if (which == HRB_TAP_OFFSETS) {
+        HRB_REQUIRE(bytes == 2 * lwlh * sizeof(int16_t), "size must be 2*flow_w*flow_h*2");
+        const int rc = launchExpandOffsets(h, t.offX, t.nWxX, ilog2(t.wsX), t.wsY ? t.offY : nullptr, t.nWxY, t.wsY ? ilog2(t.wsY) : 0,
+                                           h->offsetArrayScratch);
+        if (rc) return rc;
+        HRB_CUDA(cudaMemcpyAsync(dst, h->offsetArrayScratch, bytes, cudaMemcpyDeviceToHost, h->stream));
+    } else {
+        HRB_REQUIRE(false, "unknown tap");
+    }
+    HRB_CUDA(cudaStreamSynchronize(h->stream));
+    return HRB_OK;
+}
+
+int hrb_ofc_read_buffer(hrb_ofc* h, int which, void* dst, size_t bytes) {
+    HRB_REQUIRE(h && dst, "null argument");
+    HRB_CUDA(cudaSetDevice(h->device));
+    const size_t flowBytes = 2 * (size_t)h->flowWidth * h->flowHeight * sizeof(int16_t);
+    if (which == HRB_BUF_OFFSET_ARRAY) {
+        HRB_REQUIRE(bytes == flowBytes, "size must be 2*flow_w*flow_h*2");
+        if (!h->haveFlowLevels) {
+            setLastError("[hopperrender_b200] hrb_ofc_read_buffer: no flow has been calculated yet");
+            return HRB_ERR_STATE;
+        }
+        const int s = ilog2(h->lastWs);
+        const int rc = launchExpandOffsets(h, h->levelOffsets[h->lastIterParity][0], h->lastNWx, s, h->levelOffsets[h->lastIterParity][1], h->lastNWx, s,
+                                           h->offsetArrayScratch);
+        if (rc) return rc;
+        HRB_CUDA(cudaMemcpyAsync(dst, h->offsetArrayScratch, bytes, cudaMemcpyDeviceToHost, h->stream));
+    } else if (which == HRB_BUF_FLOW_FOR_WARP || which == HRB_BUF_FLOW_LATEST) {
+        HRB_REQUIRE(bytes == flowBytes, "size must be 2*flow_w*flow_h*2");
+        HRB_CUDA(cudaMemcpyAsync(dst, h->blurredOffsetArray[which == HRB_BUF_FLOW_FOR_WARP ? 0 : 1], bytes, cudaMemcpyDeviceToHost, h->stream));
+    } else if (which == HRB_BUF_OUTPUT_FRAME) {
+        HRB_REQUIRE(bytes <= h->outFrameBytes, "size larger than the output frame");
+        HRB_CUDA(cudaMemcpyAsync(dst, h->outputFrameArray, bytes, cudaMemcpyDeviceToHost, h->stream));
+    } else if (which == HRB_BUF_RAW_FRAME_DELTA) {
+        HRB_REQUIRE(bytes == sizeof(uint32_t), "size must be 4");
+        HRB_CUDA(cudaMemcpyAsync(dst, h->rawDeltaDev, bytes, cudaMemcpyDeviceToHost, h->stream));
+    } else {
+        HRB_REQUIRE(false, "unknown buffer");
+    }
+    HRB_CUDA(cudaStreamSynchronize(h->stream));
+    return resolveFlow(h);
+}
+
+int hrb_ofc_write_flow(hrb_ofc* h, int which, const int16_t* src, size_t count) {
+    HRB_REQUIRE(h && src, "null argument");
+    HRB_REQUIRE(which == HRB_BUF_FLOW_FOR_WARP || which == HRB_BUF_FLOW_LATEST, "only the blurred flows are writable");
+    HRB_REQUIRE(count == 2 * (size_t)h->flowWidth * h->flowHeight, "count must be 2*flow_w*flow_h");
+    HRB_CUDA(cudaSetDevice(h->device));
+    HRB_CUDA(cudaMemcpyAsync(h->blurredOffsetArray[which == HRB_BUF_FLOW_FOR_WARP ? 0 : 1], src, count * sizeof(int16_t), cudaMemcpyHostToDevice, h->stream));
+    HRB_CUDA(cudaStreamSynchronize(h->stream));
+    return HRB_OK;
+}
+
+// ---- measurement -----------------------------------------------------------------------------------
+int hrb_ofc_set_profile(hrb_ofc* h, int on) {
+    HRB_REQUIRE(h, "null handle");
+    HRB_CUDA(cudaSetDevice(h->device));
+    const int rc = profResolve(h);
+    if (rc) return rc;
+    h->prof.on = on != 0;
+    return HRB_OK;
+}
+
+int hrb_ofc_profile_read(hrb_ofc* h, hrb_ofc_profile* out) {
+    HRB_REQUIRE(h && out, "null argument");
+    HRB_CUDA(cudaSetDevice(h->device));
+    const int rc = profResolve(h);
+    if (rc) return rc;
+    out->ms_ingest = h->prof.ms[CLS_INGEST];
+    out->ms_search = h->prof.ms[CLS_SEARCH];
+    out->ms_blur = h->prof.ms[CLS_BLUR];
+    out->ms_warp = h->prof.ms[CLS_WARP];
+    out->ms_copy = h->prof.ms[CLS_COPY];
+    out->n_ingest = h->prof.n[CLS_INGEST];
+    out->n_search = h->prof.n[CLS_SEARCH];
+    out->n_blur = h->prof.n[CLS_BLUR];
+    out->n_warp = h->prof.n[CLS_WARP];
+    out->n_copy = h->prof.n[CLS_COPY];
+    return HRB_OK;
+}
+
+int hrb_ofc_profile_reset(hrb_ofc* h) {
+    HRB_REQUIRE(h, "null handle");
+    const int rc = profResolve(h);
+    if (rc) return rc;
+    for (int i = 0; i < 5; ++i) {
+        h->prof.ms[i] = 0;
+        h->prof.n[i] = 0;
+    }
+    return HRB_OK;
+}
+
+uint64_t hrb_kernel_launch_count(void) { return g_launchCount; }
+
+int hrb_microbench_sad_peak(int device_ordinal, double* giga_absdiff_per_s) {
+    HRB_REQUIRE(giga_absdiff_per_s, "null argument");
+    return microbenchSad(device_ordinal, giga_absdiff_per_s);
+}
+
+const char* hrb_last_error(void) { return t_lastError.c_str(); }
+const char* hrb_version(void) { return "hopperrender_b200 0.1 (sm_100a)"; }
+
+}  // extern "C"

@@ -1,0 +1,166 @@
+// hrb_internal.cuh — shared declarations of the hopperrender_b200 CUDA library (sm_100a).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <string>
+#include <vector>
+
+#include "hrb.h"
+
+namespace hrb {
+
+// ------------------------------------------------------------------------------------------------
+// error plumbing (replaces CHECK_ERROR, HopperRender/opticalFlowCalc.h:15-22: no exceptions here,
+// the C++ shim in include/opticalFlowCalc.h re-throws)
+// ------------------------------------------------------------------------------------------------
+void setLastError(const char* fmt, ...);
+extern unsigned long long g_launchCount;
+
+#define HRB_CUDA(call)                                                                                   \
+    do {                                                                                                 \
+        cudaError_t _e = (call);                                                                         \
+        if (_e != cudaSuccess) {                                                                         \
+            ::hrb::setLastError("[hopperrender_b200] CUDA error %d (%s) in %s at %s:%d", (int)_e,        \
+                                cudaGetErrorString(_e), __func__, __FILE__, __LINE__);                   \
+            return HRB_ERR_CUDA;                                                                         \
+        }                                                                                                \
+    } while (0)
+
+#define HRB_LAUNCH_CHECK()                                                                               \
+    do {                                                                                                 \
+        ::hrb::g_launchCount++;                                                                          \
+        HRB_CUDA(cudaGetLastError());                                                                    \
+    } while (0)
+
+// ------------------------------------------------------------------------------------------------
+// geometry of one search pass (one (iteration, step) of HopperRender/opticalFlowCalcSDR.cpp:72-107)
+// ------------------------------------------------------------------------------------------------
+struct PassGeom {
+    int windowSize;  // ws (power of two >= 2)
+    int wsLog2;
+    int iteration;
+    int step;
+    int nWx, nWy;        // windows of this level: ceil(lw/ws), ceil(lh/ws)
+    int prevNWx, prevNWy;  // windows of the parent level (ws*2); 0 at iteration 0
+};
+
+// Arguments of the search kernels.  Window-level offset arrays replace the per-pixel offsetArray of the
+// reference (offsets are constant inside each window).
+struct SearchArgs {
+    const uint32_t* plane1;  // search plane of frame N-1 (m_inputFrameArray[1]): {Y,U,V,0} per luma pixel
+    const uint32_t* plane2;  // search plane of frame N   (m_inputFrameArray[2])
+    int pitch;               // words per search-plane row
+    int W, H;                // frame size
+    int lw, lh;              // flow size
+    int rs;                  // resolution scalar
+    int ws, wsLog2, iteration;
+    int deltaScalar, neighborBiasScalar;
+    int nWx, nWy, prevNWx;
+    const int16_t* prevX;  // level i-1 offsets (nullptr at iteration 0: all zero)
+    const int16_t* prevY;
+    int16_t* curX;         // level i offsets: written by step 0, read by step 1
+    int16_t* curY;         // level i offsets: written by step 1
+    uint32_t* winSums;     // [nW][16] scratch for windows larger than one CTA tile
+    uint32_t* rawDelta;    // non-null in pass 0: receives sums[R/2-1][window 0]
+    uint32_t* tapSums;     // optional [R][nWy][nWx]
+    uint8_t* tapLayer;     // optional [nWy][nWx]
+};
+
+struct PassTapDev {
+    PassGeom g;
+    uint32_t* sums = nullptr;
+    uint8_t* layer = nullptr;
+    int16_t* offX = nullptr;  // snapshot of the X offsets after the pass
+    int16_t* offY = nullptr;
+    int wsX = 0, nWxX = 0, nWyX = 0;  // level geometry of the X snapshot
+    int wsY = 0, nWxY = 0, nWyY = 0;  // level geometry of the Y snapshot (0 = all zero)
+};
+
+struct Profile {
+    bool on = false;
+    struct Pending {
+        cudaEvent_t a, b;
+        int cls;
+    };
+    std::vector<Pending> pending;
+    std::vector<cudaEvent_t> pool;
+    double ms[5] = {0, 0, 0, 0, 0};
+    unsigned long long n[5] = {0, 0, 0, 0, 0};
+};
+enum { CLS_INGEST = 0, CLS_SEARCH = 1, CLS_BLUR = 2, CLS_WARP = 3, CLS_COPY = 4 };
+
+}  // namespace hrb
+
+// The handle.  Field names mirror HopperRender/opticalFlowCalc.h:26-78 where a counterpart exists.
+struct hrb_ofc {
+    // video properties
+    int frameWidth, frameHeight, inputStride, outputStride;
+    float outputBlackLevel, outputWhiteLevel;
+    int hdr, bpp;
+    // optical flow calculation
+    int resScalar, flowWidth, flowHeight, searchRadius;
+    double ofcCalcTime, ofcAvgCalcTime, ofcPeakCalcTime;
+    int ofcCalcCount;
+    double ofcCalcTimeSum, warpCalcTime;
+    int deltaScalar, neighborBiasScalar;
+    unsigned int totalFrameDelta, frameCount;
+
+    // CUDA
+    int device;
+    cudaStream_t stream;
+    bool ownStream;
+    // one record per calculateOpticalFlow in flight: m_ofcStartedEvent / ofcEndEvent of the reference plus the
+    // pinned word that receives the raw frame delta; a small ring lets the asynchronous path run ahead of the GPU
+    struct FlowRecord {
+        cudaEvent_t start, end;
+        uint32_t* rawDeltaHost;
+        bool startValid, pending;
+    };
+    static constexpr int kFlowRecords = 4;
+    FlowRecord flowRec[kFlowRecords];
+    int curRec;
+    cudaEvent_t warpStartedEvent, warpEndEvent, uploadDoneEvent;
+    bool warpStartedValid;
+
+    // device arrays
+    size_t inFrameBytes, outFrameBytes;
+    uint8_t* inputFrameArray[3];   // raw NV12 / P010 frames, rotated like m_inputFrameArray
+    uint32_t* searchPlane[3];      // packed 8-bit search representation of the same slot
+    int planePitch;                // words
+    uint8_t* outputFrameArray;
+    int16_t* levelOffsets[2][2];   // [iteration parity][axis] window-level offsets
+    size_t levelCapacity;          // entries per level array
+    uint32_t* winSums;
+    int16_t* offsetArrayScratch;   // [2][lh][lw], materialised on demand for taps
+    int16_t* blurredOffsetArray[2];
+    uint32_t* rawDeltaDev;
+    // final level geometry after the last calculate (input of blur / offset tap)
+    int lastIterParity, lastNWx, lastNWy, lastWs;
+    bool haveFlowLevels;
+
+    // taps / profiling
+    bool tapMode;
+    std::vector<hrb::PassTapDev> taps;
+    hrb::Profile prof;
+};
+
+namespace hrb {
+
+// kernels_frame.cu
+int launchPackFrame(hrb_ofc* h, int slot);
+int launchCopyFrame(hrb_ofc* h, int slot);
+int launchWarpFrame(hrb_ofc* h, float t, int mode);
+// kernels_search.cu
+int launchSearchPass(hrb_ofc* h, const SearchArgs& a, int R, int step);
+int launchBlurFlow(hrb_ofc* h, const int16_t* lvlX, const int16_t* lvlY, int nWx, int wsLog2, int16_t* out);
+int launchExpandOffsets(hrb_ofc* h, const int16_t* lvlX, int nWxX, int wsLog2X, const int16_t* lvlY, int nWxY, int wsLog2Y,
+                        int16_t* out);
+int microbenchSad(int device, double* gigaAbsdiffPerSec);
+
+// profiling helpers (hrb_api.cu)
+void profBegin(hrb_ofc* h, int cls);
+void profEnd(hrb_ofc* h, int cls, unsigned launches);
+
+}  // namespace hrb

@@ -1,0 +1,448 @@
+// kernels_search.cu — the pyramidal block-matching search and the flow blur.
+//
+// One search pass = calcDeltaSumsKernel + determineLowestLayerKernel + adjustOffsetArrayKernel of the
+// reference (HopperRender/opticalFlowCalcSDR.cpp:72-107) for one (iteration, step).  The design uses
+// three facts:
+//   * the search only looks at 8-bit data, so both frames are pre-packed into {Y,U,V,0} words and one
+//     VABSDIFF4.U8.ACC evaluates the reference's 3-term delta for one pixel-candidate;
+//   * offsets are constant inside each aligned window, so they live in per-window arrays and the
+//     offset / neighbour bias of a window is (pixel count) x (a per-window constant);
+//   * sums are uint32 modulo 2^32, so any summation order is bit-exact.
+// Nothing is zero-filled or materialised per flow pixel: windows that fit a CTA tile are reduced and
+// arg-min'ed inside the SAD kernel; larger windows go through R atomics per tile and a tiny finalize.
+#include "hrb_internal.cuh"
+
+namespace hrb {
+
+namespace {
+
+constexpr int TILE = 32;  // flow pixels per CTA tile edge
+
+// sq(d) = d*d*sign(d) — calcDeltaSumsKernelSDR.h:70-71 / adjustOffsetArrayKernelSDR.h:18
+__host__ __device__ constexpr int signedSquare(int d) { return d * d * (d > 0 ? 1 : -1); }
+template <int R> __host__ __device__ constexpr int candOffset(int z) { return signedSquare(z - R / 2); }
+
+// single reflection + clamp — calcDeltaSumsKernelSDR.h:86-95
+__device__ __forceinline__ int mirrorSearch(int n, int dim) {
+    if (n >= dim) {
+        n = dim - (n - dim + 1);
+    } else if (n < 0) {
+        n = -n - 1;
+    }
+    return min(max(n, 0), dim - 1);
+}
+
+// d = sum_i |a.b[i] - b.b[i]| + c : one VABSDIFF4.U8.ACC
+__device__ __forceinline__ uint32_t sad4(uint32_t a, uint32_t b, uint32_t c) {
+    uint32_t d;
+    asm("vabsdiff4.u32.u32.u32.add %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+    return d;
+}
+
+struct WindowCtx {
+    int o;          // current offset of the window along the axis of this step
+    uint32_t nw;    // in-range flow pixels of the window
+    int nb[4];      // neighbour offsets along the axis (down, right, left, up)
+    bool useNb;
+};
+
+template <int STEP> __device__ __forceinline__ void loadWindowOffsets(const SearchArgs& a, int wx, int wy, int& ox, int& oy) {
+    const int pidx = (wy >> 1) * a.prevNWx + (wx >> 1);
+    if (STEP == 0) {
+        ox = a.prevX ? a.prevX[pidx] : 0;
+    } else {
+        ox = a.curX[wy * a.nWx + wx];
+    }
+    oy = a.prevY ? a.prevY[pidx] : 0;
+}
+
+template <int STEP> __device__ __forceinline__ WindowCtx loadWindowCtx(const SearchArgs& a, int wx, int wy, int ox, int oy) {
+    WindowCtx c;
+    c.o = STEP == 0 ? ox : oy;
+    const int x0 = wx << a.wsLog2, y0 = wy << a.wsLog2;
+    c.nw = (uint32_t)((min(x0 + a.ws, a.lw) - x0) * (min(y0 + a.ws, a.lh) - y0));
+    c.useNb = a.iteration >= 4;  // FIRST_NEIGHBOR_ITERATION, calcDeltaSumsKernelSDR.h:3,112
+    if (c.useNb) {
+        // neighbours at +-2*ws flow pixels, clamped to the array (calcDeltaSumsKernelSDR.h:6-9,114-131) = window
+        // index +-2 clamped; their offsets still have parent-level granularity.
+        const int16_t* __restrict__ p = STEP == 0 ? a.prevX : a.prevY;
+        const int wyD = min(wy + 2, a.nWy - 1), wyU = max(wy - 2, 0);
+        const int wxR = min(wx + 2, a.nWx - 1), wxL = max(wx - 2, 0);
+        c.nb[0] = p[(wyD >> 1) * a.prevNWx + (wx >> 1)];
+        c.nb[1] = p[(wy >> 1) * a.prevNWx + (wxR >> 1)];
+        c.nb[2] = p[(wy >> 1) * a.prevNWx + (wxL >> 1)];
+        c.nb[3] = p[(wyU >> 1) * a.prevNWx + (wx >> 1)];
+    } else {
+        c.nb[0] = c.nb[1] = c.nb[2] = c.nb[3] = 0;
+    }
+    return c;
+}
+
+// Window sum of layer z in the reference's terms: sum over the window's pixels of
+// (delta << deltaScalar) + offsetBias + (neighborBias << neighborBiasScalar)   (calcDeltaSumsKernelSDR.h:101-151)
+template <int R> __device__ __forceinline__ uint32_t windowTotal(const SearchArgs& a, const WindowCtx& c, uint32_t sad, int z) {
+    const int cand = (int)(short)(c.o + signedSquare(z - R / 2));
+    uint32_t bias = (uint32_t)abs(cand);
+    if (c.useNb) {
+        const uint32_t nbs = (uint32_t)abs(c.nb[0] - cand) + (uint32_t)abs(c.nb[1] - cand) + (uint32_t)abs(c.nb[2] - cand) + (uint32_t)abs(c.nb[3] - cand);
+        bias += nbs << a.neighborBiasScalar;
+    }
+    return (sad << a.deltaScalar) + c.nw * bias;
+}
+
+// determineLowestLayerKernelSDR.h:17-25 ordering: lowest sum, ties -> lowest layer
+__device__ __forceinline__ unsigned long long layerKey(uint32_t total, int z) { return ((unsigned long long)total << 32) | (unsigned)z; }
+
+// adjustOffsetArrayKernelSDR.h:14-18 applied to the window, plus the taps
+template <int R, int STEP> __device__ __forceinline__ void commitWindow(const SearchArgs& a, int wx, int wy, int o, int bestLayer) {
+    const int16_t n = (int16_t)(o + signedSquare(bestLayer - R / 2));
+    const int widx = wy * a.nWx + wx;
+    if (STEP == 0)
+        a.curX[widx] = n;
+    else
+        a.curY[widx] = n;
+    if (a.tapLayer) a.tapLayer[widx] = (uint8_t)bestLayer;
+}
+
+template <int R> __device__ __forceinline__ void tapTotal(const SearchArgs& a, int wx, int wy, int z, uint32_t total) {
+    if (a.tapSums) a.tapSums[((size_t)z * a.nWy + wy) * a.nWx + wx] = total;
+    // m_totalFrameDelta's raw value: layer R/2-1 of the first window of the first pass (opticalFlowCalcSDR.cpp:92)
+    if (a.rawDelta && wx == 0 && wy == 0 && z == R / 2 - 1) *a.rawDelta = total;
+}
+
+// Sequential finalize of one window whose R sums are in memory.
+template <int R, int STEP> __device__ __forceinline__ void finalizeWindow(const SearchArgs& a, int wx, int wy, const uint32_t* sums) {
+    int ox, oy;
+    loadWindowOffsets<STEP>(a, wx, wy, ox, oy);
+    const WindowCtx c = loadWindowCtx<STEP>(a, wx, wy, ox, oy);
+    unsigned long long best = ~0ull;
+#pragma unroll
+    for (int z = 0; z < R; ++z) {
+        const uint32_t total = windowTotal<R>(a, c, sums[z], z);
+        tapTotal<R>(a, wx, wy, z, total);
+        best = min(best, layerKey(total, z));
+    }
+    commitWindow<R, STEP>(a, wx, wy, c.o, (int)(best & 0xff));
+}
+
+// Butterfly stage of a recursive-halving reduction: lanes whose `upper` bit is clear keep the lower
+// half of their N values, the others the upper half; each receives the partner's copy of what it keeps.
+template <int N> __device__ __forceinline__ void bfly(uint32_t (&acc)[16], int mask, bool upper) {
+#pragma unroll
+    for (int i = 0; i < N / 2; ++i) {
+        const uint32_t send = upper ? acc[i] : acc[i + N / 2];
+        const uint32_t keep = upper ? acc[i + N / 2] : acc[i];
+        acc[i] = keep + __shfl_xor_sync(0xffffffffu, send, mask);
+    }
+}
+
+__device__ __forceinline__ unsigned long long shflXor64(unsigned long long v, int mask) {
+    const unsigned lo = __shfl_xor_sync(0xffffffffu, (unsigned)v, mask);
+    const unsigned hi = __shfl_xor_sync(0xffffffffu, (unsigned)(v >> 32), mask);
+    return ((unsigned long long)hi << 32) | lo;
+}
+
+// ------------------------------------------------------------------------------------------------
+// The SAD pass.  CTA = 8 warps over a TILE x TILE block of flow pixels; a warp owns 4 consecutive rows,
+// a lane one column.  R and STEP are compile-time so the candidate displacements are immediates.
+// ------------------------------------------------------------------------------------------------
+template <int R, int STEP> __global__ void __launch_bounds__(256) sadPassKernel(const SearchArgs a) {
+    __shared__ uint32_t s_sums[16][16];  // [window inside the tile][layer]
+    const int lane = threadIdx.x, warp = threadIdx.y;
+    const int tid = warp * 32 + lane;
+    const int ws = a.ws;
+    const bool small = ws <= 4;
+    if (!small) {
+        s_sums[tid >> 4][tid & 15] = 0;
+        __syncthreads();
+    }
+    const int cx = blockIdx.x * TILE + lane;
+    const int rowBase = blockIdx.y * TILE + warp * 4;
+    const int gh = ws < 4 ? ws : 4;  // rows of one accumulation group (inside one window row)
+    constexpr int LO = candOffset<R>(0), HI = candOffset<R>(R - 1);
+
+    for (int g = 0; g < 4; g += gh) {
+        const int cy0 = rowBase + g;
+        const int wx = cx >> a.wsLog2, wy = cy0 >> a.wsLog2;
+        const bool winOk = cx < a.lw && cy0 < a.lh;
+        uint32_t acc[16];
+#pragma unroll
+        for (int z = 0; z < 16; ++z) acc[z] = 0;
+        int ox = 0, oy = 0;
+        if (winOk) {
+            loadWindowOffsets<STEP>(a, wx, wy, ox, oy);
+            const int sx = cx << a.rs;
+            for (int r = 0; r < gh; ++r) {
+                const int cy = cy0 + r;
+                if (cy >= a.lh) break;
+                const int sy = cy << a.rs;
+                const uint32_t f2 = __ldg(a.plane2 + (size_t)sy * a.pitch + sx);
+                if (STEP == 0) {
+                    const uint32_t* __restrict__ row = a.plane1 + (size_t)mirrorSearch(sy + oy, a.H) * a.pitch;
+                    const int bx = sx + ox;
+                    if (bx + LO >= 0 && bx + HI < a.W) {
+                        const uint32_t* __restrict__ p = row + bx;
+#pragma unroll
+                        for (int z = 0; z < R; ++z) acc[z] = sad4(__ldg(p + candOffset<R>(z)), f2, acc[z]);
+                    } else {
+#pragma unroll
+                        for (int z = 0; z < R; ++z) acc[z] = sad4(__ldg(row + mirrorSearch(bx + candOffset<R>(z), a.W)), f2, acc[z]);
+                    }
+                } else {
+                    const uint32_t* __restrict__ col = a.plane1 + mirrorSearch(sx + ox, a.W);
+                    const int by = sy + oy;
+                    if (by + LO >= 0 && by + HI < a.H) {
+                        const uint32_t* __restrict__ p = col + (size_t)by * a.pitch;
+#pragma unroll
+                        for (int z = 0; z < R; ++z) acc[z] = sad4(__ldg(p + (ptrdiff_t)candOffset<R>(z) * a.pitch), f2, acc[z]);
+                    } else {
+#pragma unroll
+                        for (int z = 0; z < R; ++z)
+                            acc[z] = sad4(__ldg(col + (size_t)mirrorSearch(by + candOffset<R>(z), a.H) * a.pitch), f2, acc[z]);
+                    }
+                }
+            }
+        }
+
+        const bool b0 = lane & 1, b1 = lane & 2, b2 = lane & 4, b3 = lane & 8;
+        if (small) {
+            // windows of 2 or 4 lanes x gh rows: reduce inside the segment, every lane finalizes a slice of the layers
+            bfly<16>(acc, 1, b0);
+            int n = 8, zbase = b0 ? 8 : 0;
+            if (ws == 4) {
+                bfly<8>(acc, 2, b1);
+                n = 4;
+                zbase += b1 ? 4 : 0;
+            }
+            WindowCtx c;
+            c.o = 0;
+            if (winOk) c = loadWindowCtx<STEP>(a, wx, wy, ox, oy);
+            unsigned long long best = ~0ull;
+            if (winOk) {
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    const int z = zbase + i;
+                    if (i < n && z < R) {
+                        const uint32_t total = windowTotal<R>(a, c, acc[i], z);
+                        tapTotal<R>(a, wx, wy, z, total);
+                        best = min(best, layerKey(total, z));
+                    }
+                }
+            }
+            best = min(best, shflXor64(best, 1));
+            if (ws == 4) best = min(best, shflXor64(best, 2));
+            if (winOk && (lane & (ws - 1)) == 0) commitWindow<R, STEP>(a, wx, wy, c.o, (int)(best & 0xff));
+        } else {
+            // windows of >= 8 lanes: reduce over min(ws, 32) lanes, then accumulate in shared memory
+            bfly<16>(acc, 1, b0);
+            bfly<8>(acc, 2, b1);
+            bfly<4>(acc, 4, b2);
+            int z0 = (b0 ? 8 : 0) + (b1 ? 4 : 0) + (b2 ? 2 : 0);
+            int lwin = 0;
+            if (ws <= TILE) lwin = ((cy0 - blockIdx.y * TILE) >> a.wsLog2) * (TILE >> a.wsLog2) + (lane >> a.wsLog2);
+            if (ws == 8) {
+                atomicAdd(&s_sums[lwin][z0], acc[0]);
+                atomicAdd(&s_sums[lwin][z0 + 1], acc[1]);
+            } else {
+                bfly<2>(acc, 8, b3);
+                z0 += b3 ? 1 : 0;
+                if (ws == 16) {
+                    atomicAdd(&s_sums[lwin][z0], acc[0]);
+                } else {
+                    acc[0] += __shfl_xor_sync(0xffffffffu, acc[0], 16);
+                    if (lane < 16) atomicAdd(&s_sums[lwin][z0], acc[0]);
+                }
+            }
+        }
+    }
+
+    if (!small) {
+        __syncthreads();
+        if (ws <= TILE) {
+            const int perEdge = TILE >> a.wsLog2;
+            if (tid < perEdge * perEdge) {
+                const int wx = blockIdx.x * perEdge + (tid % perEdge);
+                const int wy = blockIdx.y * perEdge + (tid / perEdge);
+                if (wx < a.nWx && wy < a.nWy) finalizeWindow<R, STEP>(a, wx, wy, s_sums[tid]);
+            }
+        } else if (tid < R) {
+            const int wx = (blockIdx.x * TILE) >> a.wsLog2, wy = (blockIdx.y * TILE) >> a.wsLog2;
+            atomicAdd(&a.winSums[(size_t)(wy * a.nWx + wx) * 16 + tid], s_sums[0][tid]);
+        }
+    }
+}
+
+// arg-min + offset update for windows larger than a CTA tile
+template <int R, int STEP> __global__ void __launch_bounds__(128) finalizeLargeKernel(const SearchArgs a) {
+    const int w = blockIdx.x * blockDim.x + threadIdx.x;
+    if (w >= a.nWx * a.nWy) return;
+    uint32_t sums[R];
+#pragma unroll
+    for (int z = 0; z < R; ++z) sums[z] = a.winSums[(size_t)w * 16 + z];
+    finalizeWindow<R, STEP>(a, w % a.nWx, w / a.nWx, sums);
+}
+
+template <int R> int launchPassR(hrb_ofc* h, const SearchArgs& a, int step, unsigned* launches) {
+    const dim3 block(32, 8, 1);
+    const dim3 grid((a.lw + TILE - 1) / TILE, (a.lh + TILE - 1) / TILE, 1);
+    const bool large = a.ws > TILE;
+    if (large) HRB_CUDA(cudaMemsetAsync(a.winSums, 0, (size_t)a.nWx * a.nWy * 16 * sizeof(uint32_t), h->stream));
+    if (step == 0)
+        sadPassKernel<R, 0><<<grid, block, 0, h->stream>>>(a);
+    else
+        sadPassKernel<R, 1><<<grid, block, 0, h->stream>>>(a);
+    HRB_LAUNCH_CHECK();
+    *launches = 1;
+    if (large) {
+        const int nW = a.nWx * a.nWy;
+        if (step == 0)
+            finalizeLargeKernel<R, 0><<<(nW + 127) / 128, 128, 0, h->stream>>>(a);
+        else
+            finalizeLargeKernel<R, 1><<<(nW + 127) / 128, 128, 0, h->stream>>>(a);
+        HRB_LAUNCH_CHECK();
+        *launches = 2;
+    }
+    return HRB_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// blurFlowKernel — blurFlowKernelSDR.h:17-92: 8x8 box (taps -4..+3), mirrored borders, int sum / 64.
+// Reads the window-level offsets of the last pass directly (value of flow pixel (x,y) = level[y>>s][x>>s]).
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ int mirrorBlur(int pos, int dim) {  // blurFlowKernelSDR.h:7-14
+    if (pos >= dim) return dim - (pos - dim + 1);
+    if (pos < 0) return -pos - 1;
+    return pos;
+}
+
+constexpr int BT = 32;          // outputs per tile edge
+constexpr int BIN = BT + 7;     // input rows / columns a tile needs
+
+__global__ void __launch_bounds__(256) blurFlowKernel(const int16_t* __restrict__ lvlX, const int16_t* __restrict__ lvlY, int nWx, int wsLog2,
+                                                     int16_t* __restrict__ out, int lw, int lh) {
+    __shared__ int16_t s_in[BIN][BIN + 1];
+    __shared__ int s_h[BIN][BT];
+    const int16_t* __restrict__ lvl = blockIdx.z == 0 ? lvlX : lvlY;
+    const int X0 = blockIdx.x * BT, Y0 = blockIdx.y * BT;
+    const int tid = threadIdx.y * 32 + threadIdx.x;
+    for (int i = tid; i < BIN * BIN; i += 256) {
+        const int r = i / BIN, c = i % BIN;
+        const int y = min(max(mirrorBlur(Y0 - 4 + r, lh), 0), lh - 1);
+        const int x = min(max(mirrorBlur(X0 - 4 + c, lw), 0), lw - 1);
+        s_in[r][c] = lvl[(y >> wsLog2) * nWx + (x >> wsLog2)];
+    }
+    __syncthreads();
+    for (int i = tid; i < BIN * BT; i += 256) {
+        const int r = i / BT, c = i % BT;
+        int s = 0;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) s += s_in[r][c + k];
+        s_h[r][c] = s;
+    }
+    __syncthreads();
+    const int x = X0 + threadIdx.x;
+    if (x >= lw) return;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const int ly = threadIdx.y * 4 + j;
+        const int y = Y0 + ly;
+        if (y >= lh) break;
+        int s = 0;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) s += s_h[ly + k][threadIdx.x];
+        out[(size_t)blockIdx.z * lw * lh + (size_t)y * lw + x] = (int16_t)(s / 64);
+    }
+}
+
+// per-pixel offsetArray [2][lh][lw] from window-level arrays (test taps only)
+__global__ void expandOffsetsKernel(const int16_t* __restrict__ lvlX, int nWxX, int sX, const int16_t* __restrict__ lvlY, int nWxY, int sY,
+                                    int16_t* __restrict__ out, int lw, int lh) {
+    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y;
+    if (x >= lw || y >= lh) return;
+    out[(size_t)y * lw + x] = lvlX ? lvlX[(y >> sX) * nWxX + (x >> sX)] : (int16_t)0;
+    out[(size_t)lw * lh + (size_t)y * lw + x] = lvlY ? lvlY[(y >> sY) * nWxY + (x >> sY)] : (int16_t)0;
+}
+
+// peak-issue microbenchmark of the packed SAD instruction: 8 independent accumulator chains per thread
+__global__ void __launch_bounds__(256) sadPeakKernel(uint32_t* out, uint32_t seed, int iters) {
+    uint32_t a0 = seed + threadIdx.x, a1 = a0 * 3u, a2 = a0 * 5u, a3 = a0 * 7u, a4 = a0 * 11u, a5 = a0 * 13u, a6 = a0 * 17u, a7 = a0 * 19u;
+    const uint32_t b = seed * 0x9e3779b9u + blockIdx.x;
+    uint32_t c0 = 0, c1 = 0, c2 = 0, c3 = 0, c4 = 0, c5 = 0, c6 = 0, c7 = 0;
+    for (int i = 0; i < iters; ++i) {
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            c0 = sad4(a0, b, c0); c1 = sad4(a1, b, c1); c2 = sad4(a2, b, c2); c3 = sad4(a3, b, c3);
+            c4 = sad4(a4, b, c4); c5 = sad4(a5, b, c5); c6 = sad4(a6, b, c6); c7 = sad4(a7, b, c7);
+        }
+        a0 ^= c7;  // keeps the loop from being hoisted; 1 extra op per 64 SADs
+    }
+    out[blockIdx.x * blockDim.x + threadIdx.x] = c0 + c1 + c2 + c3 + c4 + c5 + c6 + c7;
+}
+
+}  // namespace
+
+int launchSearchPass(hrb_ofc* h, const SearchArgs& a, int R, int step) {
+    unsigned launches = 0;
+    int rc = HRB_OK;
+    profBegin(h, CLS_SEARCH);
+    switch (R) {
+#define HRB_CASE(N) case N: rc = launchPassR<N>(h, a, step, &launches); break;
+        HRB_CASE(5) HRB_CASE(6) HRB_CASE(7) HRB_CASE(8) HRB_CASE(9) HRB_CASE(10) HRB_CASE(11) HRB_CASE(12) HRB_CASE(13) HRB_CASE(14)
+        HRB_CASE(15) HRB_CASE(16) HRB_CASE(2) HRB_CASE(3) HRB_CASE(4)
+#undef HRB_CASE
+        default:
+            setLastError("[hopperrender_b200] search radius %d outside 2..16", R);
+            return HRB_ERR_INVALID_ARG;
+    }
+    profEnd(h, CLS_SEARCH, launches);
+    return rc;
+}
+
+int launchBlurFlow(hrb_ofc* h, const int16_t* lvlX, const int16_t* lvlY, int nWx, int wsLog2, int16_t* out) {
+    const dim3 block(32, 8, 1);
+    const dim3 grid((h->flowWidth + BT - 1) / BT, (h->flowHeight + BT - 1) / BT, 2);
+    profBegin(h, CLS_BLUR);
+    blurFlowKernel<<<grid, block, 0, h->stream>>>(lvlX, lvlY, nWx, wsLog2, out, h->flowWidth, h->flowHeight);
+    HRB_LAUNCH_CHECK();
+    profEnd(h, CLS_BLUR, 1);
+    return HRB_OK;
+}
+
+int launchExpandOffsets(hrb_ofc* h, const int16_t* lvlX, int nWxX, int wsLog2X, const int16_t* lvlY, int nWxY, int wsLog2Y, int16_t* out) {
+    const dim3 block(32, 8, 1);
+    const dim3 grid((h->flowWidth + 31) / 32, (h->flowHeight + 7) / 8, 1);
+    expandOffsetsKernel<<<grid, block, 0, h->stream>>>(lvlX, nWxX, wsLog2X, lvlY, nWxY, wsLog2Y, out, h->flowWidth, h->flowHeight);
+    HRB_LAUNCH_CHECK();
+    return HRB_OK;
+}
+
+int microbenchSad(int device, double* gigaAbsdiffPerSec) {
+    HRB_CUDA(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    HRB_CUDA(cudaGetDeviceProperties(&prop, device));
+    const int blocks = prop.multiProcessorCount * 8, threads = 256, iters = 4096;
+    uint32_t* d = nullptr;
+    HRB_CUDA(cudaMalloc(&d, (size_t)blocks * threads * sizeof(uint32_t)));
+    cudaEvent_t e0, e1;
+    HRB_CUDA(cudaEventCreate(&e0));
+    HRB_CUDA(cudaEventCreate(&e1));
+    float best = 1e30f;
+    for (int rep = 0; rep < 5; ++rep) {
+        HRB_CUDA(cudaEventRecord(e0, 0));
+        sadPeakKernel<<<blocks, threads>>>(d, 12345u + rep, iters);
+        HRB_LAUNCH_CHECK();
+        HRB_CUDA(cudaEventRecord(e1, 0));
+        HRB_CUDA(cudaEventSynchronize(e1));
+        float ms = 0;
+        HRB_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+        if (rep > 0 && ms < best) best = ms;
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    cudaFree(d);
+    const double sads = (double)blocks * threads * (double)iters * 64.0;  // SAD instructions (lane level)
+    *gigaAbsdiffPerSec = sads * 4.0 / (best * 1e-3) / 1e9;
+    return HRB_OK;
+}
+
+}  // namespace hrb

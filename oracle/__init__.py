@@ -1,0 +1,5 @@
+"""CPU oracle binding — TEST INFRASTRUCTURE ONLY (see oracle/hr_oracle.cpp).
+
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may import this.
+"""
+from .binding import OracleCalc, kernels, lib_path, num_threads  # noqa: F401

@@ -1,0 +1,221 @@
+"""ctypes binding of oracle/libhr_oracle.so (the CPU restatement of the reference path)."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+def lib_path():
+    return os.path.join(_HERE, "libhr_oracle.so")
+
+
+class _State(C.Structure):
+    _fields_ = [
+        ("frameWidth", C.c_int), ("frameHeight", C.c_int), ("inputStride", C.c_int), ("outputStride", C.c_int),
+        ("outputBlackLevel", C.c_float), ("outputWhiteLevel", C.c_float),
+        ("resScalar", C.c_int), ("flowWidth", C.c_int), ("flowHeight", C.c_int), ("searchRadius", C.c_int),
+        ("ofcCalcTime", C.c_double), ("ofcAvgCalcTime", C.c_double), ("ofcPeakCalcTime", C.c_double), ("warpCalcTime", C.c_double),
+        ("deltaScalar", C.c_int), ("neighborBiasScalar", C.c_int), ("totalFrameDelta", C.c_uint), ("frameCount", C.c_uint),
+    ]
+
+
+_lib = None
+
+
+def _load():
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(lib_path()):
+        subprocess.check_call(["make", "-C", _HERE, "libhr_oracle.so"])
+    lib = C.CDLL(lib_path())
+    P = C.c_void_p
+    lib.orc_ofc_create.restype = P
+    lib.orc_ofc_create.argtypes = [C.c_int] * 6 + [C.c_float, C.c_float, C.c_int, C.c_int]
+    lib.orc_ofc_destroy.argtypes = [P]
+    lib.orc_ofc_update_frame.argtypes = [P, P]
+    lib.orc_ofc_download_frame.argtypes = [P, P]
+    lib.orc_ofc_calculate_optical_flow.argtypes = [P]
+    lib.orc_ofc_warp_frames.argtypes = [P, C.c_float, C.c_int]
+    lib.orc_ofc_warp_frames.restype = C.c_int
+    lib.orc_ofc_copy_frame.argtypes = [P]
+    lib.orc_ofc_get_state.argtypes = [P, C.POINTER(_State)]
+    lib.orc_ofc_set_params.argtypes = [P, C.c_int, C.c_int, C.c_int, C.c_float, C.c_float]
+    lib.orc_ofc_set_frame_count.argtypes = [P, C.c_uint]
+    lib.orc_ofc_enable_taps.argtypes = [P, C.c_int]
+    lib.orc_ofc_num_passes.argtypes = [P]
+    lib.orc_ofc_pass_info.argtypes = [P, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int)]
+    lib.orc_ofc_read_pass_tap.argtypes = [P, C.c_int, C.c_int, P, C.c_size_t]
+    lib.orc_ofc_read_buffer.argtypes = [P, C.c_int, P, C.c_size_t]
+    lib.orc_ofc_write_flow.argtypes = [P, C.c_int, P, C.c_size_t]
+    lib.orc_calc_delta_sums.argtypes = [P, P, P, P] + [C.c_int] * 13
+    lib.orc_determine_lowest_layer.argtypes = [P, P] + [C.c_int] * 4
+    lib.orc_adjust_offset_array.argtypes = [P, P] + [C.c_int] * 5
+    lib.orc_blur_flow.argtypes = [P, P, C.c_int, C.c_int]
+    lib.orc_warp_frame.argtypes = [P, P, P, P, C.c_float, C.c_float] + [C.c_int] * 8 + [C.c_float, C.c_float, C.c_int, C.c_int]
+    lib.orc_copy_frame_kernel.argtypes = [P, P] + [C.c_int] * 4 + [C.c_float, C.c_float, C.c_int, C.c_int]
+    lib.orc_num_threads.restype = C.c_int
+    _lib = lib
+    return lib
+
+
+def num_threads():
+    return int(_load().orc_num_threads())
+
+
+def _p(a):
+    assert a.flags["C_CONTIGUOUS"]
+    return C.c_void_p(a.ctypes.data)
+
+
+class kernels:
+    """The six reference kernels as stateless functions on numpy arrays."""
+
+    @staticmethod
+    def calc_delta_sums(frame1, frame2, offsets, dimY, dimX, stride, ws, R, rs, iteration, step, deltaScalar, nbScalar, hdr):
+        _, lh, lw = offsets.shape
+        sums = np.zeros((R, lh, lw), np.uint32)
+        _load().orc_calc_delta_sums(_p(sums), _p(frame1), _p(frame2), _p(offsets), dimY, dimX, stride, lh, lw, ws, R, rs, iteration, step,
+                                    deltaScalar, nbScalar, int(hdr))
+        return sums
+
+    @staticmethod
+    def determine_lowest_layer(sums, layers, ws):
+        R, lh, lw = sums.shape
+        _load().orc_determine_lowest_layer(_p(sums), _p(layers), ws, R, lh, lw)
+        return layers
+
+    @staticmethod
+    def adjust_offset_array(offsets, layers, ws, R, step):
+        _, lh, lw = offsets.shape
+        _load().orc_adjust_offset_array(_p(offsets), _p(layers), ws, R, lh, lw, step)
+        return offsets
+
+    @staticmethod
+    def blur_flow(offsets):
+        _, lh, lw = offsets.shape
+        out = np.empty_like(offsets)
+        _load().orc_blur_flow(_p(offsets), _p(out), lh, lw)
+        return out
+
+    @staticmethod
+    def warp_frame(src12, src21, flow, out, t12, t21, H, W, S, So, rs, mode, black, white, cz, hdr):
+        _, lh, lw = flow.shape
+        _load().orc_warp_frame(_p(src12), _p(src21), _p(flow), _p(out), t12, t21, lh, lw, H, W, S, So, rs, mode, black, white, cz, int(hdr))
+        return out
+
+    @staticmethod
+    def copy_frame(src, out, H, W, S, So, black, white, cz, hdr):
+        _load().orc_copy_frame_kernel(_p(src), _p(out), H, W, S, So, black, white, cz, int(hdr))
+        return out
+
+
+class OracleCalc:
+    """Same surface as hopperrender_b200.OpticalFlowCalcSDR/HDR, computed on the CPU by the oracle."""
+
+    def __init__(self, frameHeight, frameWidth, inputStride, outputStride, deltaScalar, neighborScalar, blackLevel, whiteLevel,
+                 maxCalcRes, hdr):
+        self._lib = _load()
+        self.hdr = bool(hdr)
+        self._h = C.c_void_p(self._lib.orc_ofc_create(frameHeight, frameWidth, inputStride, outputStride, deltaScalar, neighborScalar,
+                                                      blackLevel, whiteLevel, maxCalcRes, int(hdr)))
+        s = self.state()
+        bpp = 2 if hdr else 1
+        self.inputFrameBytes = (s.frameHeight * s.inputStride + (s.frameHeight // 2) * s.inputStride) * bpp
+        self.outputFrameBytes = (s.frameHeight * s.outputStride + (s.frameHeight // 2) * s.outputStride) * bpp
+
+    def close(self):
+        if self._h:
+            self._lib.orc_ofc_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def state(self):
+        s = _State()
+        self._lib.orc_ofc_get_state(self._h, C.byref(s))
+        return s
+
+    def updateFrame(self, a):
+        assert a.nbytes >= self.inputFrameBytes
+        self._lib.orc_ofc_update_frame(self._h, _p(a))
+
+    def downloadFrame(self, a):
+        assert a.nbytes >= self.outputFrameBytes
+        self._lib.orc_ofc_download_frame(self._h, _p(a))
+
+    def calculateOpticalFlow(self):
+        self._lib.orc_ofc_calculate_optical_flow(self._h)
+
+    def warpFrames(self, t, mode):
+        if self._lib.orc_ofc_warp_frames(self._h, float(t), int(mode)):
+            raise RuntimeError("[HopperRender] Error in function warpFrames")
+
+    def copyFrame(self):
+        self._lib.orc_ofc_copy_frame(self._h)
+
+    def setParams(self, searchRadius=None, deltaScalar=None, neighborBiasScalar=None, black=None, white=None):
+        s = self.state()
+        self._lib.orc_ofc_set_params(self._h, s.searchRadius if searchRadius is None else searchRadius,
+                                     s.deltaScalar if deltaScalar is None else deltaScalar,
+                                     s.neighborBiasScalar if neighborBiasScalar is None else neighborBiasScalar,
+                                     s.outputBlackLevel if black is None else black, s.outputWhiteLevel if white is None else white)
+
+    def setFrameCount(self, n):
+        self._lib.orc_ofc_set_frame_count(self._h, n)
+
+    def enableTaps(self, on=True):
+        self._lib.orc_ofc_enable_taps(self._h, int(on))
+
+    def numPasses(self):
+        return self._lib.orc_ofc_num_passes(self._h)
+
+    def passInfo(self, p):
+        v = [C.c_int() for _ in range(3)]
+        assert self._lib.orc_ofc_pass_info(self._h, p, *[C.byref(x) for x in v]) == 0
+        return dict(zip(("windowSize", "iteration", "step"), (x.value for x in v)))
+
+    def _shape(self):
+        s = self.state()
+        return s.flowHeight, s.flowWidth
+
+    def readPassSums(self, p, R):
+        lh, lw = self._shape()
+        a = np.empty((R, lh, lw), np.uint32)
+        assert self._lib.orc_ofc_read_pass_tap(self._h, p, 0, _p(a), a.nbytes) == 0
+        return a
+
+    def readPassLayers(self, p):
+        lh, lw = self._shape()
+        a = np.empty((lh, lw), np.uint8)
+        assert self._lib.orc_ofc_read_pass_tap(self._h, p, 1, _p(a), a.nbytes) == 0
+        return a
+
+    def readPassOffsets(self, p):
+        lh, lw = self._shape()
+        a = np.empty((2, lh, lw), np.int16)
+        assert self._lib.orc_ofc_read_pass_tap(self._h, p, 2, _p(a), a.nbytes) == 0
+        return a
+
+    def _readFlow(self, which):
+        lh, lw = self._shape()
+        a = np.empty((2, lh, lw), np.int16)
+        assert self._lib.orc_ofc_read_buffer(self._h, which, _p(a), a.nbytes) == 0
+        return a
+
+    def readOffsetArray(self):
+        return self._readFlow(0)
+
+    def readFlow(self, latest=False):
+        return self._readFlow(2 if latest else 1)
+
+    def writeFlow(self, flow, latest=False):
+        flow = np.ascontiguousarray(flow, np.int16)
+        assert self._lib.orc_ofc_write_flow(self._h, 2 if latest else 1, _p(flow), flow.size) == 0

@@ -1,0 +1,54 @@
+"""The C-ABI library loads on a CPU-only machine and exports every symbol include/hrb.h declares."""
+import ctypes
+import os
+import re
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def declared_symbols():
+    src = open(os.path.join(ROOT, "include", "hrb.h")).read()
+    return sorted(set(re.findall(r"HRB_API\s+[\w\s\*]+?\b(hrb_\w+)\s*\(", src)))
+
+
+def test_header_declares_the_reference_surface():
+    names = declared_symbols()
+    # the five virtuals + ctor/dtor of HopperRender/opticalFlowCalc.h:100-132
+    for n in ["hrb_ofc_create", "hrb_ofc_destroy", "hrb_ofc_update_frame", "hrb_ofc_download_frame", "hrb_ofc_calculate_optical_flow",
+              "hrb_ofc_warp_frames", "hrb_ofc_copy_frame", "hrb_ofc_get_state", "hrb_ofc_set_params", "hrb_last_error"]:
+        assert n in names
+
+
+def test_library_exports_every_declared_symbol():
+    from hopperrender_b200 import _lib
+    lib = ctypes.CDLL(_lib.LIB_PATH)
+    for n in declared_symbols():
+        assert hasattr(lib, n), f"libhrb.so does not export {n}"
+    assert set(declared_symbols()) == set(_lib.PROTOTYPES), "python prototypes and hrb.h differ"
+
+
+def test_no_cpu_fallback_without_device():
+    """Without a GPU the product must fail loudly, not compute on the CPU."""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    import hopperrender_b200 as hr
+    with pytest.raises(RuntimeError, match="no CUDA device|CUDA error"):
+        hr.OpticalFlowCalcSDR(64, 64, 0, 0, 8, 6, 0.0, 255.0, 270)
+
+
+def test_product_does_not_reference_the_oracle():
+    """Nothing under hopperrender_b200/ or include/ may import, link or call oracle/."""
+    bad = []
+    for base in ("hopperrender_b200", "include"):
+        for dp, _, fns in os.walk(os.path.join(ROOT, base)):
+            for fn in fns:
+                if fn.endswith((".py", ".cu", ".cuh", ".h", ".cpp", "Makefile")):
+                    txt = open(os.path.join(dp, fn), errors="replace").read()
+                    if re.search(r"\boracle\b", txt) and not fn == "_lib.py":
+                        bad.append(os.path.join(dp, fn))
+                    if fn == "_lib.py" and re.search(r"import\s+oracle|from\s+oracle", txt):
+                        bad.append(os.path.join(dp, fn))
+    assert not bad, bad

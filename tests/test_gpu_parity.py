@@ -1,0 +1,270 @@
+"""GPU parity: the CUDA path (through the C ABI) against the CPU oracle on the same inputs.
+
+Bars (BASELINE.json north_star): delta sums, lowest-layer indices and offset arrays bit-exact; blurred
+flow and output pixels within +-1 LSB — we assert exact equality everywhere except the HSV
+visualisation (atan2), where one 8-bit step is allowed on a vanishing fraction of samples.
+"""
+import numpy as np
+import pytest
+
+from conftest import make_pair, out_array
+
+pytestmark = pytest.mark.gpu
+
+
+def frames(synth, W, H, hdr, n, stride=None, kind="scene", seed=0):
+    if kind == "scene":
+        return [synth.make_frame(W, H, t, synth.SEED_BASE + seed, hdr, stride) for t in range(n)]
+    if kind == "random":
+        return [synth.make_random_frame(W, H, 1000 + seed + t, hdr, stride) for t in range(n)]
+    if kind == "identical":
+        f = synth.make_frame(W, H, 0, synth.SEED_BASE + seed, hdr, stride)
+        return [f.copy() for _ in range(n)]
+    if kind == "ramp":
+        return [synth.make_ramp_frame(W, H, 5 * t, hdr, stride) for t in range(n)]
+    raise ValueError(kind)
+
+
+def rep_view(full, ws):
+    """[R][lh][lw] reference-shaped sums -> values at the window representatives [R][nWy][nWx]."""
+    return full[..., ::ws, ::ws]
+
+
+@pytest.mark.parametrize("hdr", [False, True])
+@pytest.mark.parametrize("W,H,inS,outS", [(64, 48, 0, 0), (130, 70, 192, 160), (258, 146, 258, 262)])
+@pytest.mark.parametrize("black,white", [(0.0, 255.0), (16.0, 235.0), (3.5, 200.25)])
+def test_copy_frame(synth, hdr, W, H, inS, outS, black, white):
+    g, o = make_pair(hdr, H, W, inS, outS, black=black, white=white)
+    f = frames(synth, W, H, hdr, 3, inS or None, "random")
+    for i, fr in enumerate(f):
+        g.updateFrame(fr)
+        o.updateFrame(fr)
+        g.copyFrame()
+        o.copyFrame()
+        a, b = out_array(g, hdr), out_array(o, hdr)
+        g.downloadFrame(a)
+        o.downloadFrame(b)
+        S = outS or W
+        a2, b2 = a.reshape(-1, S)[:, :W], b.reshape(-1, S)[:, :W]
+        assert np.array_equal(a2, b2), f"frame {i}: {np.count_nonzero(a2 != b2)} samples differ"
+
+
+def _smooth_flow(lh, lw, rng, amp):
+    base = rng.integers(-amp, amp + 1, (2, (lh + 7) // 8 + 1, (lw + 7) // 8 + 1))
+    fl = np.repeat(np.repeat(base, 8, 1), 8, 2)[:, :lh, :lw]
+    fl = fl + rng.integers(-2, 3, fl.shape)
+    return fl.astype(np.int16)
+
+
+@pytest.mark.parametrize("hdr", [False, True])
+@pytest.mark.parametrize("mode", [0, 1, 2, 3, 4, 5, 6])
+@pytest.mark.parametrize("W,H,maxres,inS,outS", [(64, 48, 270, 0, 0), (130, 70, 35, 136, 144), (256, 144, 36, 0, 320), (320, 176, 22, 0, 0)])
+def test_warp_modes(synth, hdr, mode, W, H, maxres, inS, outS):
+    g, o = make_pair(hdr, H, W, inS, outS, black=4.0, white=250.0, maxres=maxres)
+    for fr in frames(synth, W, H, hdr, 3, inS or None):
+        g.updateFrame(fr)
+        o.updateFrame(fr)
+    lh, lw = g.m_opticalFlowFrameHeight, g.m_opticalFlowFrameWidth
+    rng = np.random.default_rng(W * 7 + mode)
+    for amp, t in [(0, 0.5), (9, 0.0), (9, 1.0 / 6.0), (40, 0.4), (300, 0.5), (9, 1.0)]:
+        fl = _smooth_flow(lh, lw, rng, amp)
+        g.writeFlow(fl)
+        o.writeFlow(fl)
+        g.warpFrames(t, mode)
+        o.warpFrames(t, mode)
+        a, b = out_array(g, hdr), out_array(o, hdr)
+        g.downloadFrame(a)
+        o.downloadFrame(b)
+        S = outS or W
+        a2, b2 = a.reshape(-1, S)[:, :W].astype(np.int64), b.reshape(-1, S)[:, :W].astype(np.int64)
+        if mode == 3:
+            step = 256 if hdr else 1  # the visualisation is quantised to 8 bits (<< 8 in HDR chroma, << 7 luma)
+            d = np.abs(a2 - b2)
+            assert d.max() <= step and np.count_nonzero(d) <= max(4, d.size // 500), (d.max(), np.count_nonzero(d))
+        else:
+            assert np.array_equal(a2, b2), f"mode {mode} amp {amp} t {t}: {np.count_nonzero(a2 != b2)} differ, max {np.abs(a2 - b2).max()}"
+
+
+def test_warp_rejects_blend_above_one(synth):
+    g, o = make_pair(False, 48, 64)
+    with pytest.raises(RuntimeError):
+        g.warpFrames(1.5, 2)
+    with pytest.raises(RuntimeError):
+        o.warpFrames(1.5, 2)
+
+
+SEARCH_CASES = [
+    # hdr, W, H, maxres, inS, R, kind
+    (False, 64, 48, 270, 0, 5, "scene"),
+    (False, 64, 48, 270, 0, 16, "random"),
+    (True, 64, 48, 270, 80, 11, "scene"),
+    (False, 130, 70, 270, 0, 6, "scene"),
+    (True, 130, 70, 270, 0, 16, "random"),
+    (False, 258, 146, 73, 272, 16, "scene"),    # rs = 1, odd flow size 129x73
+    (True, 512, 288, 72, 0, 16, "scene"),       # rs = 2, flow 128x72
+    (False, 320, 200, 270, 0, 16, "identical"),
+    (False, 320, 200, 270, 0, 9, "ramp"),
+    (True, 384, 224, 270, 0, 16, "scene"),
+    (False, 16, 16, 270, 0, 5, "random"),
+]
+
+
+@pytest.mark.parametrize("hdr,W,H,maxres,inS,R,kind", SEARCH_CASES)
+def test_search_ladder_taps(synth, hdr, W, H, maxres, inS, R, kind):
+    """Every pass of the ladder: window sums, arg-min layers and offsets are bit-exact."""
+    g, o = make_pair(hdr, H, W, inS, 0, maxres=maxres, R=R)
+    g.setTapMode(True)
+    o.enableTaps(True)
+    for fr in frames(synth, W, H, hdr, 3, inS or None, kind):
+        g.updateFrame(fr)
+        o.updateFrame(fr)
+    g.calculateOpticalFlow()
+    o.calculateOpticalFlow()
+    assert g.numPasses() == o.numPasses() > 0
+    for p in range(o.numPasses()):
+        gi, oi = g.passInfo(p), o.passInfo(p)
+        assert (gi["windowSize"], gi["iteration"], gi["step"]) == (oi["windowSize"], oi["iteration"], oi["step"])
+        ws = oi["windowSize"]
+        s_ref = rep_view(o.readPassSums(p, R), ws)
+        s_gpu = g.readPassSums(p, R)
+        assert s_gpu.shape == s_ref.shape
+        assert np.array_equal(s_gpu, s_ref), f"pass {p} (ws {ws}): {np.count_nonzero(s_gpu != s_ref)} window sums differ"
+        l_ref = o.readPassLayers(p)[::ws, ::ws]
+        assert np.array_equal(g.readPassLayers(p), l_ref), f"pass {p}: layers differ"
+        assert np.array_equal(g.readPassOffsets(p), o.readPassOffsets(p)), f"pass {p}: offsets differ"
+    assert np.array_equal(g.readOffsetArray(), o.readOffsetArray())
+    assert np.array_equal(g.readFlow(latest=True), o.readFlow(latest=True)), "blurred flow differs"
+    assert g.m_totalFrameDelta == o.state().totalFrameDelta
+
+
+@pytest.mark.parametrize("hdr,W,H,maxres,R", [(False, 1920, 1080, 270, 16), (False, 1920, 1080, 540, 16), (True, 960, 540, 2160, 5)])
+def test_search_final_flow_midsize(synth, hdr, W, H, maxres, R):
+    """BASELINE configs 1 and 2 at full size (and a quarter-size full-resolution HDR case): final flow bit-exact."""
+    g, o = make_pair(hdr, H, W, maxres=maxres, R=R)
+    for fr in frames(synth, W, H, hdr, 3):
+        g.updateFrame(fr)
+        o.updateFrame(fr)
+    g.calculateOpticalFlow()
+    o.calculateOpticalFlow()
+    assert np.array_equal(g.readOffsetArray(), o.readOffsetArray())
+    assert np.array_equal(g.readFlow(latest=True), o.readFlow(latest=True))
+    assert g.m_totalFrameDelta == o.state().totalFrameDelta
+
+
+@pytest.mark.parametrize("hdr", [False, True])
+def test_filter_sequence(synth, hdr):
+    """The filter's call order (HopperRender.cpp:953-1186) over several source frames: every delivered frame matches."""
+    W, H = 192, 112
+    g, o = make_pair(hdr, H, W, 0, 200, maxres=270, R=8)
+    blend = 0.0
+    for t, fr in enumerate(frames(synth, W, H, hdr, 6)):
+        g.updateFrame(fr)
+        o.updateFrame(fr)
+        if g.m_frameCount >= 3:
+            g.calculateOpticalFlow()
+            o.calculateOpticalFlow()
+            assert g.m_totalFrameDelta == o.state().totalFrameDelta
+        for _ in range(3):
+            if g.m_frameCount >= 3:
+                g.warpFrames(blend, 2)
+                o.warpFrames(blend, 2)
+            else:
+                g.copyFrame()
+                o.copyFrame()
+            a, b = out_array(g, hdr), out_array(o, hdr)
+            g.downloadFrame(a)
+            o.downloadFrame(b)
+            a2, b2 = a.reshape(-1, 200)[:, :W], b.reshape(-1, 200)[:, :W]
+            assert np.array_equal(a2, b2), f"source frame {t}, blend {blend}"
+            blend += 0.4
+            if blend >= 1.0:
+                blend -= 1.0
+    assert g.m_frameCount == o.state().frameCount == 6
+    assert g.m_ofcCalcTime > 0 and g.m_warpCalcTime > 0
+
+
+def test_live_parameter_updates(synth):
+    """Fields the filter writes on a live object take effect at the next call (HopperRender.cpp:1386-1389,1448)."""
+    W, H = 128, 96
+    g, o = make_pair(False, H, W, R=5)
+    fs = frames(synth, W, H, False, 4)
+    for fr in fs[:3]:
+        g.updateFrame(fr)
+        o.updateFrame(fr)
+    for R, ds, ns, bl, wh in [(5, 8, 6, 0.0, 255.0), (6, 4, 2, 10.0, 240.0), (16, 10, 0, 0.0, 128.0), (7, 0, 10, 20.0, 255.0)]:
+        g.m_opticalFlowSearchRadius = R
+        g.m_deltaScalar = ds
+        g.m_neighborBiasScalar = ns
+        g.m_outputBlackLevel = bl
+        g.m_outputWhiteLevel = wh
+        o.setParams(R, ds, ns, bl, wh)
+        g.calculateOpticalFlow()
+        o.calculateOpticalFlow()
+        g.calculateOpticalFlow()   # twice, so that the flow warpFrames reads is the one just computed
+        o.calculateOpticalFlow()
+        assert np.array_equal(g.readFlow(), o.readFlow())
+        g.warpFrames(0.5, 2)
+        o.warpFrames(0.5, 2)
+        a, b = out_array(g, False), out_array(o, False)
+        g.downloadFrame(a)
+        o.downloadFrame(b)
+        assert np.array_equal(a, b)
+    g.m_frameCount = 0
+    assert g.m_frameCount == 0
+
+
+def test_device_resident_and_async_paths(synth):
+    """update_frame_device / calculate_async / download_async give the same bytes as the blocking calls."""
+    import torch
+    W, H = 256, 144
+    g, o = make_pair(True, H, W, R=16)
+    out_pinned = torch.zeros(g.outputFrameBytes // 2, dtype=torch.int16).pin_memory()
+    for fr in frames(synth, W, H, True, 4):
+        dev = torch.from_numpy(fr.view(np.int16)).cuda()
+        torch.cuda.synchronize()
+        g.updateFrameDevice(dev)
+        o.updateFrame(fr)
+        if g.m_frameCount >= 3:
+            g.calculateOpticalFlowAsync()
+            o.calculateOpticalFlow()
+            g.warpFrames(0.25, 2)
+            o.warpFrames(0.25, 2)
+            g.downloadFrameAsync(out_pinned)
+            g.synchronize()
+            b = out_array(o, True)
+            o.downloadFrame(b)
+            assert np.array_equal(out_pinned.numpy().view(np.uint16), b)
+            assert g.m_totalFrameDelta == o.state().totalFrameDelta
+
+
+def test_full_size_4k_p010_properties(synth):
+    """BASELINE config 3 (3840x2160 P010, full-resolution flow, R=16): against the oracle at full size, plus
+    size-independent properties (identical frames -> zero flow and pass-through blend)."""
+    W, H = 3840, 2160
+    g, o = make_pair(True, H, W, maxres=2160, R=16)
+    fs = frames(synth, W, H, True, 3)
+    for fr in fs:
+        g.updateFrame(fr)
+        o.updateFrame(fr)
+    g.calculateOpticalFlow()
+    o.calculateOpticalFlow()
+    assert g.m_totalFrameDelta == o.state().totalFrameDelta
+    fg, fo = g.readFlow(latest=True), o.readFlow(latest=True)
+    assert np.array_equal(fg, fo), f"{np.count_nonzero(fg != fo)} flow samples differ"
+    # the dominant motion of the synthetic scene is (+6,-3) px/frame => offsets (-6,+3)
+    off = g.readOffsetArray()
+    assert np.median(off[0]) == -6 and np.median(off[1]) == 3
+    g.calculateOpticalFlow()
+    o.calculateOpticalFlow()
+    g.warpFrames(0.5, 2)
+    o.warpFrames(0.5, 2)
+    a, b = out_array(g, True), out_array(o, True)
+    g.downloadFrame(a)
+    o.downloadFrame(b)
+    assert np.array_equal(a, b)
+    # identical frames: zero flow, and the blend of two identical frames is the level-corrected frame itself
+    for _ in range(3):
+        g.updateFrame(fs[0])
+    g.calculateOpticalFlow()
+    assert g.m_totalFrameDelta == 0 or g.m_totalFrameDelta < 2
+    assert not g.readOffsetArray().any()
