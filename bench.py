@@ -62,7 +62,7 @@ class ClockSampler:
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100"],
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "50"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._pump, daemon=True)
             self.thread.start()
@@ -84,7 +84,7 @@ class ClockSampler:
         sm, mx, reasons = [], [], set()
         for r in self.rows:
             c = [x.strip() for x in r.split(",")]
-            if len(c) < 7:
+            if len(c) < 7 or not self.rows:
                 continue
             try:
                 sm.append(float(c[0]))
@@ -227,7 +227,7 @@ def cpu_baseline(wl):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=60)
+    ap.add_argument("--steps", type=int, default=400)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="cfg3", choices=sorted(WORKLOADS))
@@ -271,7 +271,7 @@ def main():
     torch.cuda.synchronize()
 
     total_steps = args.warmup + args.steps
-    sched = replay.output_schedule(2 * total_steps + 8, wl["target"], replay.SOURCE_FRAME_TIME_23976)
+    sched = replay.output_schedule(5 * total_steps + 128, wl["target"], replay.SOURCE_FRAME_TIME_23976)
 
     def barrier():
         if world > 1:
@@ -317,10 +317,14 @@ def main():
         step_device(idx)
         idx += 1
     calc.synchronize()
-    barrier()
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
+        for _ in range(args.warmup):  # a little more load while nvidia-smi starts sampling
+            step_device(idx)
+            idx += 1
+        calc.synchronize()
+    barrier()
     launches0 = hr.kernel_launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     frames = 0

@@ -164,13 +164,14 @@ template <int R, int STEP> __global__ void __launch_bounds__(256) sadPassKernel(
     for (int g = 0; g < 4; g += gh) {
         const int cy0 = rowBase + g;
         const int wx = cx >> a.wsLog2, wy = cy0 >> a.wsLog2;
-        const bool winOk = cx < a.lw && cy0 < a.lh;
+        const bool pixOk = cx < a.lw && cy0 < a.lh;                          // this lane has pixels to accumulate
+        const bool winOk = (wx << a.wsLog2) < a.lw && cy0 < a.lh;            // this lane's window exists (it may finalize a slice of it)
         uint32_t acc[16];
 #pragma unroll
         for (int z = 0; z < 16; ++z) acc[z] = 0;
         int ox = 0, oy = 0;
-        if (winOk) {
-            loadWindowOffsets<STEP>(a, wx, wy, ox, oy);
+        if (winOk) loadWindowOffsets<STEP>(a, wx, wy, ox, oy);
+        if (pixOk) {
             const int sx = cx << a.rs;
             for (int r = 0; r < gh; ++r) {
                 const int cy = cy0 + r;

@@ -23,6 +23,37 @@ class _State(C.Structure):
 
 
 _lib = None
+_ref_lib = None
+
+
+class _Api:
+    """The calculator entry points of one library under a common name (oracle: orc_*, oracle/_ref: hrref_*)."""
+
+    def __init__(self, lib, prefix):
+        P = C.c_void_p
+        sig = {
+            "ofc_create": (P, [C.c_int] * 6 + [C.c_float, C.c_float, C.c_int, C.c_int]),
+            "ofc_destroy": (None, [P]),
+            "ofc_update_frame": (C.c_int, [P, P]),
+            "ofc_download_frame": (C.c_int, [P, P]),
+            "ofc_calculate_optical_flow": (C.c_int, [P]),
+            "ofc_warp_frames": (C.c_int, [P, C.c_float, C.c_int]),
+            "ofc_copy_frame": (C.c_int, [P]),
+            "ofc_get_state": (None, [P, C.POINTER(_State)]),
+            "ofc_set_params": (None, [P, C.c_int, C.c_int, C.c_int, C.c_float, C.c_float]),
+            "ofc_set_frame_count": (None, [P, C.c_uint]),
+            "ofc_enable_taps": (None, [P, C.c_int]),
+            "ofc_num_passes": (C.c_int, [P]),
+            "ofc_pass_info": (C.c_int, [P, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int)]),
+            "ofc_read_pass_tap": (C.c_int, [P, C.c_int, C.c_int, P, C.c_size_t]),
+            "ofc_read_buffer": (C.c_int, [P, C.c_int, P, C.c_size_t]),
+            "ofc_write_flow": (C.c_int, [P, C.c_int, P, C.c_size_t]),
+        }
+        for name, (res, args) in sig.items():
+            fn = getattr(lib, prefix + name)
+            fn.restype = res
+            fn.argtypes = args
+            setattr(self, name, fn)
 
 
 def _load():
@@ -33,24 +64,7 @@ def _load():
         subprocess.check_call(["make", "-C", _HERE, "libhr_oracle.so"])
     lib = C.CDLL(lib_path())
     P = C.c_void_p
-    lib.orc_ofc_create.restype = P
-    lib.orc_ofc_create.argtypes = [C.c_int] * 6 + [C.c_float, C.c_float, C.c_int, C.c_int]
-    lib.orc_ofc_destroy.argtypes = [P]
-    lib.orc_ofc_update_frame.argtypes = [P, P]
-    lib.orc_ofc_download_frame.argtypes = [P, P]
-    lib.orc_ofc_calculate_optical_flow.argtypes = [P]
-    lib.orc_ofc_warp_frames.argtypes = [P, C.c_float, C.c_int]
-    lib.orc_ofc_warp_frames.restype = C.c_int
-    lib.orc_ofc_copy_frame.argtypes = [P]
-    lib.orc_ofc_get_state.argtypes = [P, C.POINTER(_State)]
-    lib.orc_ofc_set_params.argtypes = [P, C.c_int, C.c_int, C.c_int, C.c_float, C.c_float]
-    lib.orc_ofc_set_frame_count.argtypes = [P, C.c_uint]
-    lib.orc_ofc_enable_taps.argtypes = [P, C.c_int]
-    lib.orc_ofc_num_passes.argtypes = [P]
-    lib.orc_ofc_pass_info.argtypes = [P, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int)]
-    lib.orc_ofc_read_pass_tap.argtypes = [P, C.c_int, C.c_int, P, C.c_size_t]
-    lib.orc_ofc_read_buffer.argtypes = [P, C.c_int, P, C.c_size_t]
-    lib.orc_ofc_write_flow.argtypes = [P, C.c_int, P, C.c_size_t]
+    lib.api = _Api(lib, "orc_")
     lib.orc_calc_delta_sums.argtypes = [P, P, P, P] + [C.c_int] * 13
     lib.orc_determine_lowest_layer.argtypes = [P, P] + [C.c_int] * 4
     lib.orc_adjust_offset_array.argtypes = [P, P] + [C.c_int] * 5
@@ -116,20 +130,28 @@ class kernels:
 class OracleCalc:
     """Same surface as hopperrender_b200.OpticalFlowCalcSDR/HDR, computed on the CPU by the oracle."""
 
+    def _api(self):
+        return _load().api
+
     def __init__(self, frameHeight, frameWidth, inputStride, outputStride, deltaScalar, neighborScalar, blackLevel, whiteLevel,
                  maxCalcRes, hdr):
-        self._lib = _load()
+        self._lib = self._api()
         self.hdr = bool(hdr)
-        self._h = C.c_void_p(self._lib.orc_ofc_create(frameHeight, frameWidth, inputStride, outputStride, deltaScalar, neighborScalar,
-                                                      blackLevel, whiteLevel, maxCalcRes, int(hdr)))
+        self._h = C.c_void_p(self._lib.ofc_create(frameHeight, frameWidth, inputStride, outputStride, deltaScalar, neighborScalar,
+                                                  blackLevel, whiteLevel, maxCalcRes, int(hdr)))
+        if not self._h:
+            raise RuntimeError("calculator construction failed: " + self._last_error())
         s = self.state()
         bpp = 2 if hdr else 1
         self.inputFrameBytes = (s.frameHeight * s.inputStride + (s.frameHeight // 2) * s.inputStride) * bpp
         self.outputFrameBytes = (s.frameHeight * s.outputStride + (s.frameHeight // 2) * s.outputStride) * bpp
 
+    def _last_error(self):
+        return ""
+
     def close(self):
         if self._h:
-            self._lib.orc_ofc_destroy(self._h)
+            self._lib.ofc_destroy(self._h)
             self._h = None
 
     def __del__(self):
@@ -140,46 +162,50 @@ class OracleCalc:
 
     def state(self):
         s = _State()
-        self._lib.orc_ofc_get_state(self._h, C.byref(s))
+        self._lib.ofc_get_state(self._h, C.byref(s))
         return s
+
+    def _chk(self, rc, what):
+        if rc:
+            raise RuntimeError(f"{what} failed: {self._last_error()}")
 
     def updateFrame(self, a):
         assert a.nbytes >= self.inputFrameBytes
-        self._lib.orc_ofc_update_frame(self._h, _p(a))
+        self._chk(self._lib.ofc_update_frame(self._h, _p(a)), "updateFrame")
 
     def downloadFrame(self, a):
         assert a.nbytes >= self.outputFrameBytes
-        self._lib.orc_ofc_download_frame(self._h, _p(a))
+        self._chk(self._lib.ofc_download_frame(self._h, _p(a)), "downloadFrame")
 
     def calculateOpticalFlow(self):
-        self._lib.orc_ofc_calculate_optical_flow(self._h)
+        self._chk(self._lib.ofc_calculate_optical_flow(self._h), "calculateOpticalFlow")
 
     def warpFrames(self, t, mode):
-        if self._lib.orc_ofc_warp_frames(self._h, float(t), int(mode)):
-            raise RuntimeError("[HopperRender] Error in function warpFrames")
+        if self._lib.ofc_warp_frames(self._h, float(t), int(mode)):
+            raise RuntimeError("[HopperRender] Error in function warpFrames " + self._last_error())
 
     def copyFrame(self):
-        self._lib.orc_ofc_copy_frame(self._h)
+        self._chk(self._lib.ofc_copy_frame(self._h), "copyFrame")
 
     def setParams(self, searchRadius=None, deltaScalar=None, neighborBiasScalar=None, black=None, white=None):
         s = self.state()
-        self._lib.orc_ofc_set_params(self._h, s.searchRadius if searchRadius is None else searchRadius,
+        self._lib.ofc_set_params(self._h, s.searchRadius if searchRadius is None else searchRadius,
                                      s.deltaScalar if deltaScalar is None else deltaScalar,
                                      s.neighborBiasScalar if neighborBiasScalar is None else neighborBiasScalar,
                                      s.outputBlackLevel if black is None else black, s.outputWhiteLevel if white is None else white)
 
     def setFrameCount(self, n):
-        self._lib.orc_ofc_set_frame_count(self._h, n)
+        self._lib.ofc_set_frame_count(self._h, n)
 
     def enableTaps(self, on=True):
-        self._lib.orc_ofc_enable_taps(self._h, int(on))
+        self._lib.ofc_enable_taps(self._h, int(on))
 
     def numPasses(self):
-        return self._lib.orc_ofc_num_passes(self._h)
+        return self._lib.ofc_num_passes(self._h)
 
     def passInfo(self, p):
         v = [C.c_int() for _ in range(3)]
-        assert self._lib.orc_ofc_pass_info(self._h, p, *[C.byref(x) for x in v]) == 0
+        assert self._lib.ofc_pass_info(self._h, p, *[C.byref(x) for x in v]) == 0
         return dict(zip(("windowSize", "iteration", "step"), (x.value for x in v)))
 
     def _shape(self):
@@ -189,25 +215,25 @@ class OracleCalc:
     def readPassSums(self, p, R):
         lh, lw = self._shape()
         a = np.empty((R, lh, lw), np.uint32)
-        assert self._lib.orc_ofc_read_pass_tap(self._h, p, 0, _p(a), a.nbytes) == 0
+        assert self._lib.ofc_read_pass_tap(self._h, p, 0, _p(a), a.nbytes) == 0
         return a
 
     def readPassLayers(self, p):
         lh, lw = self._shape()
         a = np.empty((lh, lw), np.uint8)
-        assert self._lib.orc_ofc_read_pass_tap(self._h, p, 1, _p(a), a.nbytes) == 0
+        assert self._lib.ofc_read_pass_tap(self._h, p, 1, _p(a), a.nbytes) == 0
         return a
 
     def readPassOffsets(self, p):
         lh, lw = self._shape()
         a = np.empty((2, lh, lw), np.int16)
-        assert self._lib.orc_ofc_read_pass_tap(self._h, p, 2, _p(a), a.nbytes) == 0
+        assert self._lib.ofc_read_pass_tap(self._h, p, 2, _p(a), a.nbytes) == 0
         return a
 
     def _readFlow(self, which):
         lh, lw = self._shape()
         a = np.empty((2, lh, lw), np.int16)
-        assert self._lib.orc_ofc_read_buffer(self._h, which, _p(a), a.nbytes) == 0
+        assert self._lib.ofc_read_buffer(self._h, which, _p(a), a.nbytes) == 0
         return a
 
     def readOffsetArray(self):
@@ -218,4 +244,54 @@ class OracleCalc:
 
     def writeFlow(self, flow, latest=False):
         flow = np.ascontiguousarray(flow, np.int16)
-        assert self._lib.orc_ofc_write_flow(self._h, 2 if latest else 1, _p(flow), flow.size) == 0
+        assert self._lib.ofc_write_flow(self._h, 2 if latest else 1, _p(flow), flow.size) == 0
+
+
+# ---------------------------------------------------------------------------------------------------------
+# oracle/_ref: the UNMODIFIED reference classes + kernel strings on a real OpenCL device (see oracle/ref_build)
+# ---------------------------------------------------------------------------------------------------------
+def ref_lib_path():
+    return os.path.join(_HERE, "_ref", "libhrref.so")
+
+
+def _load_ref():
+    global _ref_lib
+    if _ref_lib is not None:
+        return _ref_lib
+    if not os.path.exists(ref_lib_path()):
+        raise FileNotFoundError(f"{ref_lib_path()} not built (make -C oracle/ref_build, needs /root/reference)")
+    lib = C.CDLL(ref_lib_path())
+    lib.api = _Api(lib, "hrref_")
+    lib.hrref_last_error.restype = C.c_char_p
+    lib.hrref_opencl_library.restype = C.c_char_p
+    lib.hrref_device_name.argtypes = [C.c_void_p, C.c_char_p, C.c_size_t]
+    _ref_lib = lib
+    return lib
+
+
+class RefCalc(OracleCalc):
+    """OpticalFlowCalcSDR / OpticalFlowCalcHDR of the reference itself, run through OpenCL."""
+
+    def _api(self):
+        return _load_ref().api
+
+    def _last_error(self):
+        return _load_ref().hrref_last_error().decode("utf-8", "replace")
+
+    def deviceName(self):
+        buf = C.create_string_buffer(256)
+        _load_ref().hrref_device_name(self._h, buf, 256)
+        return buf.value.decode()
+
+    def openclLibrary(self):
+        return _load_ref().hrref_opencl_library().decode()
+
+
+def ref_available():
+    """True when oracle/_ref is built and an OpenCL device accepts the reference."""
+    try:
+        c = RefCalc(32, 32, 0, 0, 8, 6, 0.0, 255.0, 270, False)
+        c.close()
+        return True
+    except Exception:
+        return False

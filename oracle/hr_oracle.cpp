@@ -13,8 +13,11 @@
 //     representative receives the exact sum over the window's in-range work-items, mod 2^32.
 //   * the single-reflection mirror of calcDeltaSums is followed by a clamp (only differs where
 //     the reference would read out of bounds).
-//   * fp32 is IEEE, no FMA contraction (compile with -ffp-contract=off), float->integer
-//     conversions truncate, round() is half-away-from-zero.
+//   * fp32 is IEEE with correctly rounded division, float->integer conversions truncate, round() is
+//     half-away-from-zero.  No implicit FMA contraction (compile with -ffp-contract=off); the ONE
+//     contraction the reference's OpenCL build performs on NVIDIA GPUs — the blend a*t21 + b*t12 ->
+//     fma(a, t21, b*t12) — is written explicitly.  What is left is the OpenCL compiler's approximate
+//     division in apply_levelsY (not reproducible off the GPU): <= 1 LSB, luma only.
 //   * atan2 (HSV visualisation only) is evaluated in double and rounded to float.
 //
 // Parity pin: the reference ships no tests or golden vectors.  This restatement is
@@ -355,7 +358,10 @@ void warpFrame(const T* sourceFrame12, const T* sourceFrame21, const int16_t* of
             } else if (frameOutputMode == 1) {  // :174-175
                 *out = b;
             } else {  // :176-183
-                uint16_t blendedValue = (uint16_t)((float)a * frameScalar21 + (float)b * frameScalar12);
+                // OpenCL C contracts a*b+c by default; the NVIDIA OpenCL compiler emits fma(a, t21, b*t12) for this
+                // line (established against the reference run on a B200: bit-exact with this form, up to 2 LSB off
+                // without it once the levels gain exceeds 1 — see tests/test_oracle_golden.py).
+                uint16_t blendedValue = (uint16_t)fmaf((float)a, frameScalar21, (float)b * frameScalar12);
                 if (frameOutputMode == 3) {
                     blendedValue = visualizeFlow<T>((short)-offsetX12, (short)-offsetY12, (T)blendedValue, cz + (cx & (cz ? 1 : 0)),
                                                     resolutionScalar <= 2 ? 4 : 1);
@@ -513,7 +519,7 @@ void* orc_ofc_create(int frameHeight, int frameWidth, int inputStride, int outpu
 void orc_ofc_destroy(void* h) { delete (Calc*)h; }
 
 // HR/opticalFlowCalcSDR.cpp:19-29 / HDR :19-29
-void orc_ofc_update_frame(void* h, const uint8_t* inputPlanes) {
+int orc_ofc_update_frame(void* h, const uint8_t* inputPlanes) {
     Calc* c = (Calc*)h;
     c->ofcStart = std::chrono::steady_clock::now();
     const size_t n = (size_t)c->bpp * ((size_t)c->m_frameHeight * c->m_inputStride + (size_t)(c->m_frameHeight / 2) * c->m_inputStride);
@@ -523,18 +529,20 @@ void orc_ofc_update_frame(void* h, const uint8_t* inputPlanes) {
     c->in[1] = c->in[2];
     c->in[2] = t;
     c->m_frameCount++;
+    return 0;
 }
 
 // HR/opticalFlowCalcSDR.cpp:31-42
-void orc_ofc_download_frame(void* h, uint8_t* outputPlanes) {
+int orc_ofc_download_frame(void* h, uint8_t* outputPlanes) {
     Calc* c = (Calc*)h;
     const size_t n = (size_t)c->bpp * ((size_t)c->m_frameHeight * c->m_outputStride + (size_t)(c->m_frameHeight / 2) * c->m_outputStride);
     std::memcpy(outputPlanes, c->output.data(), n);
     c->m_warpCalcTime = secondsSince(c->warpStart);
+    return 0;
 }
 
 // HR/opticalFlowCalcSDR.cpp:44-139 / HDR :44-139
-void orc_ofc_calculate_optical_flow(void* h) {
+int orc_ofc_calculate_optical_flow(void* h) {
     Calc* c = (Calc*)h;
     const int lw = c->m_opticalFlowFrameWidth, lh = c->m_opticalFlowFrameHeight;
     const int R = c->m_opticalFlowSearchRadius;  // :46
@@ -591,6 +599,7 @@ void orc_ofc_calculate_optical_flow(void* h) {
     c->m_ofcCalcCount++;
     c->m_ofcCalcTimeSum += c->m_ofcCalcTime;
     if (c->m_ofcCalcTime > c->m_ofcPeakCalcTime) c->m_ofcPeakCalcTime = c->m_ofcCalcTime;
+    return 0;
 }
 
 // HR/opticalFlowCalcSDR.cpp:141-168 / HDR :141-170.  Returns non-zero where the reference throws.
@@ -613,7 +622,7 @@ int orc_ofc_warp_frames(void* h, float blendingScalar, int frameOutputMode) {
 }
 
 // HR/opticalFlowCalcSDR.cpp:170-183 / HDR :172-188
-void orc_ofc_copy_frame(void* h) {
+int orc_ofc_copy_frame(void* h) {
     Calc* c = (Calc*)h;
     const int frameIndex = c->m_frameCount >= 3 ? 0 : c->m_frameCount >= 2 ? 1 : 2;
     float black = c->m_outputBlackLevel, white = c->m_outputWhiteLevel;
@@ -625,6 +634,7 @@ void orc_ofc_copy_frame(void* h) {
     for (int cz = 0; cz < 2; ++cz)
         orc_copy_frame_kernel(c->input[c->in[frameIndex]].data(), c->output.data(), c->m_frameHeight, c->m_frameWidth, c->m_inputStride,
                               c->m_outputStride, black, white, cz, c->hdr);
+    return 0;
 }
 
 // ---- field access -------------------------------------------------------------------------------

@@ -266,5 +266,53 @@ def test_full_size_4k_p010_properties(synth):
     for _ in range(3):
         g.updateFrame(fs[0])
     g.calculateOpticalFlow()
-    assert g.m_totalFrameDelta == 0 or g.m_totalFrameDelta < 2
-    assert not g.readOffsetArray().any()
+    assert not g.readOffsetArray().any() and not g.readFlow(latest=True).any()
+    g.calculateOpticalFlow()
+    g.warpFrames(0.5, 2)
+    g.downloadFrame(a)
+    # zero flow + identical sources: the blend is the source itself up to the HDR level scale 65535/65280
+    src = fs[0][:W * H].reshape(H, W)[1:-1, 1:-1].astype(np.float32)
+    exp = np.minimum(src / np.float32(65280.0) * np.float32(65535.0), np.float32(65535.0)).astype(np.uint16)
+    assert np.array_equal(a[:W * H].reshape(H, W)[1:-1, 1:-1], exp)
+
+
+@pytest.mark.parametrize("hdr", [False, True])
+def test_cpp_shim_replay_matches_python_replay_over_the_oracle(synth, hdr, tmp_path):
+    """tools/replay.cpp drives include/opticalFlowCalc*.h (the header-compatible classes a DirectShow build would
+    use) through the filter's delivery loop; the delivered frames must be the ones the oracle produces under
+    hopperrender_b200.replay.DeliveryLoop (same loop, python)."""
+    import os
+    import subprocess
+    import zlib
+
+    from conftest import ROOT, OracleAsCalc
+    from hopperrender_b200 import replay
+    from oracle import OracleCalc
+    exe = os.path.join(ROOT, "tools", "replay_cpp.bin")
+    if not os.path.exists(exe):
+        pytest.skip("tools/replay_cpp.bin not built (python -c 'import __graft_entry__ as g; g.build()')")
+    W, H, n = 256, 144, 9
+    fs = frames(synth, W, H, hdr, n)
+    fs[6] = synth.make_random_frame(W, H, 77, hdr)  # a scene cut in the middle
+    raw = tmp_path / "frames.raw"
+    with open(raw, "wb") as f:
+        for fr in fs:
+            f.write(fr.tobytes())
+    res = subprocess.run([exe, str(raw), str(W), str(H), "1" if hdr else "0", str(n), str(replay.TARGET_FRAME_TIME_60), "270", "7"],
+                         capture_output=True, text=True, timeout=120)
+    assert res.returncode == 0, res.stderr
+    got = [ln.split() for ln in res.stdout.strip().splitlines()]
+    o = OracleAsCalc(OracleCalc(H, W, W, W, 8, 6, 0.0, 255.0, 270, hdr))
+    o.m_opticalFlowSearchRadius = 7
+    loop = replay.DeliveryLoop(o, target_frame_time=replay.TARGET_FRAME_TIME_60, auto_adjust=False)
+    exp = []
+    out = np.zeros(o.outputFrameBytes, np.uint8)
+    for fr in fs:
+        loop.deliver(fr, out, sink=lambda buf, info: exp.append((info, zlib.crc32(buf.tobytes()) & 0xFFFFFFFF)))
+    assert len(got) == len(exp) > n
+    for g_line, (info, crc) in zip(got, exp):
+        assert int(g_line[0]) == info["source"] and int(g_line[1]) == info["index"]
+        assert abs(float(g_line[2]) - info["blend"]) < 1e-8
+        assert int(g_line[3]) == int(info["warped"])
+        assert int(g_line[5], 16) == crc, f"delivered frame {g_line[:2]} differs"
+    assert any(not i["warped"] and i["source"] >= 3 for i, _ in exp), "the scene cut should have forced a copyFrame"
