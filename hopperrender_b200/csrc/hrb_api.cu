@@ -350,6 +350,7 @@ int hrb_ofc_create(hrb_ofc** out, const hrb_ofc_desc* d) {
     }
     h->haveFlowLevels = false;
     h->tapMode = false;
+    h->searchVariant = 0;
     h->lastIterParity = 0;
     h->lastNWx = h->lastNWy = h->lastWs = 0;
     for (int i = 0; i < 3; ++i) {
@@ -778,6 +779,13 @@ int hrb_ofc_profile_reset(hrb_ofc* h) {
         h->prof.ms[i] = 0;
         h->prof.n[i] = 0;
     }
+    return HRB_OK;
+}
+
+int hrb_ofc_set_search_variant(hrb_ofc* h, int variant) {
+    HRB_REQUIRE(h, "null handle");
+    HRB_REQUIRE(variant == 0 || variant == 1, "variant must be 0 (automatic) or 1 (generic kernel only)");
+    h->searchVariant = variant;
     return HRB_OK;
 }
 

@@ -141,6 +141,7 @@ struct hrb_ofc {
     bool haveFlowLevels;
 
     // taps / profiling
+    int searchVariant;  // 0: automatic kernel selection, 1: generic sadPassKernel for every pass (A/B and parity tests)
     bool tapMode;
     std::vector<hrb::PassTapDev> taps;
     hrb::Profile prof;
@@ -154,6 +155,8 @@ int launchCopyFrame(hrb_ofc* h, int slot);
 int launchWarpFrame(hrb_ofc* h, float t, int mode);
 // kernels_search.cu
 int launchSearchPass(hrb_ofc* h, const SearchArgs& a, int R, int step);
+// kernels_search_big.cu: HRB_OK, an error code, or -1 when this (R, geometry) is not covered
+int launchSearchPassBig(hrb_ofc* h, const SearchArgs& a, int R, int step);
 int launchBlurFlow(hrb_ofc* h, const int16_t* lvlX, const int16_t* lvlY, int nWx, int wsLog2, int16_t* out);
 int launchExpandOffsets(hrb_ofc* h, const int16_t* lvlX, int nWxX, int wsLog2X, const int16_t* lvlY, int nWxY, int wsLog2Y,
                         int16_t* out);

@@ -10,137 +10,11 @@
 //   * sums are uint32 modulo 2^32, so any summation order is bit-exact.
 // Nothing is zero-filled or materialised per flow pixel: windows that fit a CTA tile are reduced and
 // arg-min'ed inside the SAD kernel; larger windows go through R atomics per tile and a tiny finalize.
-#include "hrb_internal.cuh"
+#include "search_common.cuh"
 
 namespace hrb {
 
 namespace {
-
-constexpr int TILE = 32;  // flow pixels per CTA tile edge
-
-// sq(d) = d*d*sign(d) — calcDeltaSumsKernelSDR.h:70-71 / adjustOffsetArrayKernelSDR.h:18
-__host__ __device__ constexpr int signedSquare(int d) { return d * d * (d > 0 ? 1 : -1); }
-template <int R> __host__ __device__ constexpr int candOffset(int z) { return signedSquare(z - R / 2); }
-
-// single reflection + clamp — calcDeltaSumsKernelSDR.h:86-95
-__device__ __forceinline__ int mirrorSearch(int n, int dim) {
-    if (n >= dim) {
-        n = dim - (n - dim + 1);
-    } else if (n < 0) {
-        n = -n - 1;
-    }
-    return min(max(n, 0), dim - 1);
-}
-
-// d = sum_i |a.b[i] - b.b[i]| + c : one VABSDIFF4.U8.ACC
-__device__ __forceinline__ uint32_t sad4(uint32_t a, uint32_t b, uint32_t c) {
-    uint32_t d;
-    asm("vabsdiff4.u32.u32.u32.add %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
-    return d;
-}
-
-struct WindowCtx {
-    int o;          // current offset of the window along the axis of this step
-    uint32_t nw;    // in-range flow pixels of the window
-    int nb[4];      // neighbour offsets along the axis (down, right, left, up)
-    bool useNb;
-};
-
-template <int STEP> __device__ __forceinline__ void loadWindowOffsets(const SearchArgs& a, int wx, int wy, int& ox, int& oy) {
-    const int pidx = (wy >> 1) * a.prevNWx + (wx >> 1);
-    if (STEP == 0) {
-        ox = a.prevX ? a.prevX[pidx] : 0;
-    } else {
-        ox = a.curX[wy * a.nWx + wx];
-    }
-    oy = a.prevY ? a.prevY[pidx] : 0;
-}
-
-template <int STEP> __device__ __forceinline__ WindowCtx loadWindowCtx(const SearchArgs& a, int wx, int wy, int ox, int oy) {
-    WindowCtx c;
-    c.o = STEP == 0 ? ox : oy;
-    const int x0 = wx << a.wsLog2, y0 = wy << a.wsLog2;
-    c.nw = (uint32_t)((min(x0 + a.ws, a.lw) - x0) * (min(y0 + a.ws, a.lh) - y0));
-    c.useNb = a.iteration >= 4;  // FIRST_NEIGHBOR_ITERATION, calcDeltaSumsKernelSDR.h:3,112
-    if (c.useNb) {
-        // neighbours at +-2*ws flow pixels, clamped to the array (calcDeltaSumsKernelSDR.h:6-9,114-131) = window
-        // index +-2 clamped; their offsets still have parent-level granularity.
-        const int16_t* __restrict__ p = STEP == 0 ? a.prevX : a.prevY;
-        const int wyD = min(wy + 2, a.nWy - 1), wyU = max(wy - 2, 0);
-        const int wxR = min(wx + 2, a.nWx - 1), wxL = max(wx - 2, 0);
-        c.nb[0] = p[(wyD >> 1) * a.prevNWx + (wx >> 1)];
-        c.nb[1] = p[(wy >> 1) * a.prevNWx + (wxR >> 1)];
-        c.nb[2] = p[(wy >> 1) * a.prevNWx + (wxL >> 1)];
-        c.nb[3] = p[(wyU >> 1) * a.prevNWx + (wx >> 1)];
-    } else {
-        c.nb[0] = c.nb[1] = c.nb[2] = c.nb[3] = 0;
-    }
-    return c;
-}
-
-// Window sum of layer z in the reference's terms: sum over the window's pixels of
-// (delta << deltaScalar) + offsetBias + (neighborBias << neighborBiasScalar)   (calcDeltaSumsKernelSDR.h:101-151)
-template <int R> __device__ __forceinline__ uint32_t windowTotal(const SearchArgs& a, const WindowCtx& c, uint32_t sad, int z) {
-    const int cand = (int)(short)(c.o + signedSquare(z - R / 2));
-    uint32_t bias = (uint32_t)abs(cand);
-    if (c.useNb) {
-        const uint32_t nbs = (uint32_t)abs(c.nb[0] - cand) + (uint32_t)abs(c.nb[1] - cand) + (uint32_t)abs(c.nb[2] - cand) + (uint32_t)abs(c.nb[3] - cand);
-        bias += nbs << a.neighborBiasScalar;
-    }
-    return (sad << a.deltaScalar) + c.nw * bias;
-}
-
-// determineLowestLayerKernelSDR.h:17-25 ordering: lowest sum, ties -> lowest layer
-__device__ __forceinline__ unsigned long long layerKey(uint32_t total, int z) { return ((unsigned long long)total << 32) | (unsigned)z; }
-
-// adjustOffsetArrayKernelSDR.h:14-18 applied to the window, plus the taps
-template <int R, int STEP> __device__ __forceinline__ void commitWindow(const SearchArgs& a, int wx, int wy, int o, int bestLayer) {
-    const int16_t n = (int16_t)(o + signedSquare(bestLayer - R / 2));
-    const int widx = wy * a.nWx + wx;
-    if (STEP == 0)
-        a.curX[widx] = n;
-    else
-        a.curY[widx] = n;
-    if (a.tapLayer) a.tapLayer[widx] = (uint8_t)bestLayer;
-}
-
-template <int R> __device__ __forceinline__ void tapTotal(const SearchArgs& a, int wx, int wy, int z, uint32_t total) {
-    if (a.tapSums) a.tapSums[((size_t)z * a.nWy + wy) * a.nWx + wx] = total;
-    // m_totalFrameDelta's raw value: layer R/2-1 of the first window of the first pass (opticalFlowCalcSDR.cpp:92)
-    if (a.rawDelta && wx == 0 && wy == 0 && z == R / 2 - 1) *a.rawDelta = total;
-}
-
-// Sequential finalize of one window whose R sums are in memory.
-template <int R, int STEP> __device__ __forceinline__ void finalizeWindow(const SearchArgs& a, int wx, int wy, const uint32_t* sums) {
-    int ox, oy;
-    loadWindowOffsets<STEP>(a, wx, wy, ox, oy);
-    const WindowCtx c = loadWindowCtx<STEP>(a, wx, wy, ox, oy);
-    unsigned long long best = ~0ull;
-#pragma unroll
-    for (int z = 0; z < R; ++z) {
-        const uint32_t total = windowTotal<R>(a, c, sums[z], z);
-        tapTotal<R>(a, wx, wy, z, total);
-        best = min(best, layerKey(total, z));
-    }
-    commitWindow<R, STEP>(a, wx, wy, c.o, (int)(best & 0xff));
-}
-
-// Butterfly stage of a recursive-halving reduction: lanes whose `upper` bit is clear keep the lower
-// half of their N values, the others the upper half; each receives the partner's copy of what it keeps.
-template <int N> __device__ __forceinline__ void bfly(uint32_t (&acc)[16], int mask, bool upper) {
-#pragma unroll
-    for (int i = 0; i < N / 2; ++i) {
-        const uint32_t send = upper ? acc[i] : acc[i + N / 2];
-        const uint32_t keep = upper ? acc[i + N / 2] : acc[i];
-        acc[i] = keep + __shfl_xor_sync(0xffffffffu, send, mask);
-    }
-}
-
-__device__ __forceinline__ unsigned long long shflXor64(unsigned long long v, int mask) {
-    const unsigned lo = __shfl_xor_sync(0xffffffffu, (unsigned)v, mask);
-    const unsigned hi = __shfl_xor_sync(0xffffffffu, (unsigned)(v >> 32), mask);
-    return ((unsigned long long)hi << 32) | lo;
-}
 
 // ------------------------------------------------------------------------------------------------
 // The SAD pass.  CTA = 8 warps over a TILE x TILE block of flow pixels; a warp owns 4 consecutive rows,
@@ -288,11 +162,19 @@ template <int R> int launchPassR(hrb_ofc* h, const SearchArgs& a, int step, unsi
     const dim3 grid((a.lw + TILE - 1) / TILE, (a.lh + TILE - 1) / TILE, 1);
     const bool large = a.ws > TILE;
     if (large) HRB_CUDA(cudaMemsetAsync(a.winSums, 0, (size_t)a.nWx * a.nWy * 16 * sizeof(uint32_t), h->stream));
-    if (step == 0)
-        sadPassKernel<R, 0><<<grid, block, 0, h->stream>>>(a);
-    else
-        sadPassKernel<R, 1><<<grid, block, 0, h->stream>>>(a);
-    HRB_LAUNCH_CHECK();
+    bool done = false;
+    if (a.rs == 0 && a.ws >= 32 && h->searchVariant != 1) {  // sliding-window kernels (kernels_search_big.cu)
+        const int rc = launchSearchPassBig(h, a, R, step);
+        if (rc > 0) return rc;
+        done = rc == HRB_OK;
+    }
+    if (!done) {
+        if (step == 0)
+            sadPassKernel<R, 0><<<grid, block, 0, h->stream>>>(a);
+        else
+            sadPassKernel<R, 1><<<grid, block, 0, h->stream>>>(a);
+        HRB_LAUNCH_CHECK();
+    }
     *launches = 1;
     if (large) {
         const int nW = a.nWx * a.nWy;

@@ -259,6 +259,9 @@ class OpticalFlowCalc:
         return int(a[0])
 
     # ---- measurement ----------------------------------------------------------------------------------
+    def setSearchVariant(self, variant):
+        self._check(self._lib.hrb_ofc_set_search_variant(self._h, int(variant)))
+
     def setProfile(self, on):
         self._check(self._lib.hrb_ofc_set_profile(self._h, 1 if on else 0))
 

@@ -175,6 +175,9 @@ typedef struct hrb_ofc_profile {
 HRB_API int hrb_ofc_set_profile(hrb_ofc* h, int on);
 HRB_API int hrb_ofc_profile_read(hrb_ofc* h, hrb_ofc_profile* out); /* synchronizes */
 HRB_API int hrb_ofc_profile_reset(hrb_ofc* h);
+/* Kernel selection for the search ladder: 0 = automatic (sliding-window kernels where they apply), 1 = the generic
+ * kernel for every pass.  Results are identical; exists for A/B measurements and parity tests. */
+HRB_API int hrb_ofc_set_search_variant(hrb_ofc* h, int variant);
 /* number of kernels this library has launched in this process */
 HRB_API uint64_t hrb_kernel_launch_count(void);
 /* packed byte-SAD instruction peak of the device (VABSDIFF4.U8.ACC issue rate), in 1e9 byte-abs-diffs/s */

@@ -1,0 +1,91 @@
+#!/usr/bin/env python
+"""Condense ncu CSV exports (gpurun_out/prof/*) into the tracked summaries under profiles/.
+usage: python tools/ncu_summary.py <tag>"""
+import collections
+import csv
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+KEYS = [
+    "gpu__time_duration.sum", "launch__registers_per_thread", "launch__grid_size", "launch__block_size",
+    "sm__warps_active.avg.pct_of_peak_sustained_active", "sm__throughput.avg.pct_of_peak_sustained_elapsed",
+    "smsp__issue_active.avg.pct_of_peak_sustained_active", "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed",
+    "dram__bytes_read.sum", "dram__bytes_write.sum", "l1tex__t_sector_hit_rate.pct", "lts__t_sector_hit_rate.pct",
+    "smsp__inst_executed.sum", "l1tex__t_requests_pipe_lsu_mem_global_op_ld.sum", "l1tex__t_sectors_pipe_lsu_mem_global_op_ld.sum",
+    "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum", "sm__cycles_elapsed.max",
+    "smsp__average_warps_issue_stalled_long_scoreboard_per_issue_active.ratio",
+    "smsp__average_warps_issue_stalled_short_scoreboard_per_issue_active.ratio",
+    "smsp__average_warps_issue_stalled_math_pipe_throttle_per_issue_active.ratio",
+    "smsp__average_warps_issue_stalled_mio_throttle_per_issue_active.ratio",
+    "smsp__average_warps_issue_stalled_not_selected_per_issue_active.ratio",
+    "smsp__average_warps_issue_stalled_wait_per_issue_active.ratio",
+    "smsp__average_warps_issue_stalled_barrier_per_issue_active.ratio",
+]
+
+
+def short(name):
+    return name.replace("void ", "").replace("unnamed>::", "").replace("hrb::", "").split("(")[0]
+
+
+def launches(tag, out):
+    path = os.path.join(ROOT, "gpurun_out", "prof", f"launches_{tag}.csv")
+    if not os.path.exists(path):
+        return
+    rows = list(csv.reader(open(path)))
+    hdr, data = None, []
+    for r in rows:
+        if r and r[0] == "ID":
+            hdr = r
+            continue
+        if hdr and len(r) == len(hdr):
+            data.append(dict(zip(hdr, r)))
+    agg = collections.OrderedDict()
+    for d in data:
+        a = agg.setdefault(short(d["Kernel Name"]), [0, 0.0])
+        a[0] += 1
+        a[1] += float(d["Metric Value"]) / 1e3
+    bench = {k: v for k, v in agg.items() if "sadPeak" not in k}
+    tot = sum(v[1] for v in bench.values())
+    out.write(f"## launch list ({len(data)} launches, `ncu --metrics gpu__time_duration.sum --clock-control none`, cold-cache serialised: compare shares)\n\n")
+    out.write("| kernel | launches | total us | avg us | share of step kernels |\n|---|---|---|---|---|\n")
+    for k, v in sorted(bench.items(), key=lambda kv: -kv[1][1]):
+        out.write(f"| `{k}` | {v[0]} | {v[1]:.1f} | {v[1] / v[0]:.1f} | {v[1] / tot * 100:.1f}% |\n")
+    out.write("\n")
+
+
+def raw(tag, which, out, picks=None):
+    path = os.path.join(ROOT, "gpurun_out", "prof", f"{which}_raw_{tag}.csv")
+    if not os.path.exists(path):
+        return
+    rows = list(csv.reader(open(path)))
+    hdr, units, data = rows[0], rows[1], rows[2:]
+    idx = {h: i for i, h in enumerate(hdr)}
+    sel = picks if picks is not None else range(len(data))
+    sel = [i for i in sel if i < len(data)]
+    out.write(f"## `ncu --set full` — {which} ({len(data)} captured launches; shown: {list(sel)})\n\n")
+    out.write("| metric | unit | " + " | ".join(f"#{i} {short(data[i][idx['Kernel Name']])[:28]}" for i in sel) + " |\n")
+    out.write("|---|---|" + "---|" * len(sel) + "\n")
+    for k in KEYS:
+        if k not in idx:
+            continue
+        out.write(f"| {k} | {units[idx[k]]} | " + " | ".join(data[i][idx[k]] for i in sel) + " |\n")
+    out.write("\n")
+
+
+def main():
+    tag = sys.argv[1]
+    picks = [int(x) for x in sys.argv[2].split(",")] if len(sys.argv) > 2 else None
+    os.makedirs(os.path.join(ROOT, "profiles"), exist_ok=True)
+    dst = os.path.join(ROOT, "profiles", f"ncu_summary_{tag}.md")
+    with open(dst, "w") as out:
+        out.write(f"# ncu summary {tag}\n\nCommand: `python bench.py --steps 2 --warmup 3 --no-cpu-baseline` under ncu (tools/gpu_profile.sh); "
+                  "numbers taken under the profiler are for SHARES and per-kernel counters only, never bench values.\n\n")
+        launches(tag, out)
+        raw(tag, "warp", out, [0])
+        raw(tag, "sad", out, picks)
+    print("wrote", dst)
+
+
+if __name__ == "__main__":
+    main()
