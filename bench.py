@@ -179,7 +179,7 @@ def run_reference(args, wl, wl_name):
     if rank != 0:
         return
     cores = num_threads()
-    per_step = max(1.0, min(8.0, 150.0 / (args.steps + args.warmup)))
+    per_step = max(1.0, min(8.0, float(os.environ.get("HRB_REF_BUDGET_S", "150")) / max(args.steps + args.warmup, 1)))
     rows = cpu_sample_rows(wl, per_step)
     step = cpu_step_runner(wl, rows)
     for _ in range(args.warmup):
@@ -273,24 +273,17 @@ def main():
     total_steps = args.warmup + args.steps
     sched = replay.output_schedule(5 * total_steps + 128, wl["target"], replay.SOURCE_FRAME_TIME_23976)
 
+    from hopperrender_b200 import shard
+
     def barrier():
-        if world > 1:
-            dist.barrier()
+        shard.barrier()
         torch.cuda.synchronize()
 
     def max_over_ranks(ms):
-        if world > 1:
-            t = torch.tensor([ms], device="cuda", dtype=torch.float64)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            return float(t.item())
-        return ms
+        return shard.combine(0, ms)[1]
 
     def sum_over_ranks(v):
-        if world > 1:
-            t = torch.tensor([v], device="cuda", dtype=torch.float64)
-            dist.all_reduce(t, op=dist.ReduceOp.SUM)
-            return float(t.item())
-        return float(v)
+        return shard.combine(v, 0.0)[0]
 
     # ---- device-resident loop ---------------------------------------------------------------------
     def step_device(i):

@@ -164,6 +164,9 @@ static int enqueueFlow(hrb_ofc* h) {
     a.plane1 = h->searchPlane[1];  // frame1 = m_inputFrameArray[1], opticalFlowCalcSDR.cpp:79
     a.plane2 = h->searchPlane[2];  // frame2 = m_inputFrameArray[2], opticalFlowCalcSDR.cpp:80
     a.pitch = h->planePitch;
+    a.planeT1 = h->searchPlaneT[1];
+    a.planeT2 = h->searchPlaneT[2];
+    a.pitchT = h->planePitchT;
     a.W = h->frameWidth;
     a.H = h->frameHeight;
     a.lw = lw;
@@ -247,7 +250,7 @@ static int enqueueFlow(hrb_ofc* h) {
     // blur into m_blurredOffsetArray[0], then swap (opticalFlowCalcSDR.cpp:113-123)
     {
         const int rc = launchBlurFlow(h, h->levelOffsets[h->lastIterParity][0], h->levelOffsets[h->lastIterParity][1], h->lastNWx, ilog2(h->lastWs),
-                                      h->blurredOffsetArray[0]);
+                                      h->blurredOffsetArray[0], h->flowMaxDev[0]);
         if (rc) return rc;
     }
     HRB_CUDA(cudaMemcpyAsync(rec.rawDeltaHost, h->rawDeltaDev, sizeof(uint32_t), cudaMemcpyDeviceToHost, h->stream));
@@ -255,6 +258,9 @@ static int enqueueFlow(hrb_ofc* h) {
     int16_t* t0 = h->blurredOffsetArray[0];
     h->blurredOffsetArray[0] = h->blurredOffsetArray[1];
     h->blurredOffsetArray[1] = t0;
+    uint32_t* m0 = h->flowMaxDev[0];
+    h->flowMaxDev[0] = h->flowMaxDev[1];
+    h->flowMaxDev[1] = m0;
     rec.pending = true;
     return HRB_OK;
 }
@@ -269,6 +275,10 @@ static int finishUpdate(hrb_ofc* h) {
     h->searchPlane[0] = h->searchPlane[1];
     h->searchPlane[1] = h->searchPlane[2];
     h->searchPlane[2] = p0;
+    uint32_t* t0 = h->searchPlaneT[0];
+    h->searchPlaneT[0] = h->searchPlaneT[1];
+    h->searchPlaneT[1] = h->searchPlaneT[2];
+    h->searchPlaneT[2] = t0;
     h->frameCount++;
     return launchPackFrame(h, 2);
 }
@@ -351,17 +361,25 @@ int hrb_ofc_create(hrb_ofc** out, const hrb_ofc_desc* d) {
     h->haveFlowLevels = false;
     h->tapMode = false;
     h->searchVariant = 0;
+    h->warpVariant = 0;
+    h->smCount = 148;
+    {
+        cudaDeviceProp prop;
+        if (cudaGetDeviceProperties(&prop, d->device_ordinal) == cudaSuccess) h->smCount = prop.multiProcessorCount;
+    }
     h->lastIterParity = 0;
     h->lastNWx = h->lastNWy = h->lastWs = 0;
     for (int i = 0; i < 3; ++i) {
         h->inputFrameArray[i] = nullptr;
         h->searchPlane[i] = nullptr;
+        h->searchPlaneT[i] = nullptr;
     }
     h->outputFrameArray = nullptr;
     h->levelOffsets[0][0] = h->levelOffsets[0][1] = h->levelOffsets[1][0] = h->levelOffsets[1][1] = nullptr;
     h->winSums = nullptr;
     h->offsetArrayScratch = nullptr;
     h->blurredOffsetArray[0] = h->blurredOffsetArray[1] = nullptr;
+    h->flowMaxDev[0] = h->flowMaxDev[1] = nullptr;
     h->rawDeltaDev = nullptr;
     h->warpStartedEvent = h->warpEndEvent = h->uploadDoneEvent = nullptr;
 
@@ -383,9 +401,11 @@ int hrb_ofc_create(hrb_ofc** out, const hrb_ofc_desc* d) {
     h->outFrameBytes = ((size_t)h->frameHeight * h->outputStride + (size_t)(h->frameHeight / 2) * h->outputStride) * h->bpp;
     h->planePitch = (h->frameWidth + 31) & ~31;
     const size_t planeBytes = (size_t)h->planePitch * h->frameHeight * sizeof(uint32_t);
+    h->planePitchT = (h->frameHeight + 31) & ~31;
+    const size_t planeTBytes = (size_t)h->planePitchT * h->frameWidth * sizeof(uint32_t);
     h->levelCapacity = ((lw + 1) / 2) * ((lh + 1) / 2);
     const size_t winSumEntries = ((lw + 63) / 64) * ((lh + 63) / 64) * 16 + 16;
-    const size_t need = 3 * (h->inFrameBytes + planeBytes) + h->outFrameBytes + 4 * h->levelCapacity * 2 + winSumEntries * 4 + 3 * 2 * lw * lh * 2;
+    const size_t need = 3 * (h->inFrameBytes + planeBytes + planeTBytes) + h->outFrameBytes + 4 * h->levelCapacity * 2 + winSumEntries * 4 + 3 * 2 * lw * lh * 2;
 
     // replaces detectDevices' memory check (opticalFlowCalc.cpp:48-51,86-96)
     size_t freeB = 0, totalB = 0;
@@ -428,6 +448,8 @@ int hrb_ofc_create(hrb_ofc** out, const hrb_ofc_desc* d) {
         HRB_TRY(cudaMemsetAsync(h->inputFrameArray[i], 0, h->inFrameBytes, h->stream));
         HRB_TRY(cudaMalloc(&h->searchPlane[i], planeBytes));
         HRB_TRY(cudaMemsetAsync(h->searchPlane[i], 0, planeBytes, h->stream));
+        HRB_TRY(cudaMalloc(&h->searchPlaneT[i], planeTBytes));
+        HRB_TRY(cudaMemsetAsync(h->searchPlaneT[i], 0, planeTBytes, h->stream));
     }
     HRB_TRY(cudaMalloc(&h->outputFrameArray, h->outFrameBytes));
     HRB_TRY(cudaMemsetAsync(h->outputFrameArray, 0, h->outFrameBytes, h->stream));
@@ -441,6 +463,8 @@ int hrb_ofc_create(hrb_ofc** out, const hrb_ofc_desc* d) {
     for (int i = 0; i < 2; ++i) {
         HRB_TRY(cudaMalloc(&h->blurredOffsetArray[i], 2 * lw * lh * sizeof(int16_t)));
         HRB_TRY(cudaMemsetAsync(h->blurredOffsetArray[i], 0, 2 * lw * lh * sizeof(int16_t), h->stream));
+        HRB_TRY(cudaMalloc(&h->flowMaxDev[i], sizeof(uint32_t)));
+        HRB_TRY(cudaMemsetAsync(h->flowMaxDev[i], 0, sizeof(uint32_t), h->stream));
     }
     HRB_TRY(cudaMalloc(&h->rawDeltaDev, sizeof(uint32_t)));
     HRB_TRY(cudaMemsetAsync(h->rawDeltaDev, 0, sizeof(uint32_t), h->stream));
@@ -463,6 +487,7 @@ void hrb_ofc_destroy(hrb_ofc* h) {
     for (int i = 0; i < 3; ++i) {
         cudaFree(h->inputFrameArray[i]);
         cudaFree(h->searchPlane[i]);
+        cudaFree(h->searchPlaneT[i]);
     }
     cudaFree(h->outputFrameArray);
     for (int p = 0; p < 2; ++p)
@@ -471,6 +496,8 @@ void hrb_ofc_destroy(hrb_ofc* h) {
     cudaFree(h->offsetArrayScratch);
     cudaFree(h->blurredOffsetArray[0]);
     cudaFree(h->blurredOffsetArray[1]);
+    cudaFree(h->flowMaxDev[0]);
+    cudaFree(h->flowMaxDev[1]);
     cudaFree(h->rawDeltaDev);
     for (auto& r : h->flowRec) {
         if (r.rawDeltaHost) cudaFreeHost(r.rawDeltaHost);
@@ -738,7 +765,14 @@ int hrb_ofc_write_flow(hrb_ofc* h, int which, const int16_t* src, size_t count) 
     HRB_REQUIRE(which == HRB_BUF_FLOW_FOR_WARP || which == HRB_BUF_FLOW_LATEST, "only the blurred flows are writable");
     HRB_REQUIRE(count == 2 * (size_t)h->flowWidth * h->flowHeight, "count must be 2*flow_w*flow_h");
     HRB_CUDA(cudaSetDevice(h->device));
-    HRB_CUDA(cudaMemcpyAsync(h->blurredOffsetArray[which == HRB_BUF_FLOW_FOR_WARP ? 0 : 1], src, count * sizeof(int16_t), cudaMemcpyHostToDevice, h->stream));
+    const int slot = which == HRB_BUF_FLOW_FOR_WARP ? 0 : 1;
+    HRB_CUDA(cudaMemcpyAsync(h->blurredOffsetArray[slot], src, count * sizeof(int16_t), cudaMemcpyHostToDevice, h->stream));
+    uint32_t peak = 0;
+    for (size_t i = 0; i < count; ++i) {
+        const uint32_t v = (uint32_t)(src[i] < 0 ? -(int)src[i] : (int)src[i]);
+        if (v > peak) peak = v;
+    }
+    HRB_CUDA(cudaMemcpyAsync(h->flowMaxDev[slot], &peak, sizeof(uint32_t), cudaMemcpyHostToDevice, h->stream));
     HRB_CUDA(cudaStreamSynchronize(h->stream));
     return HRB_OK;
 }
@@ -784,8 +818,9 @@ int hrb_ofc_profile_reset(hrb_ofc* h) {
 
 int hrb_ofc_set_search_variant(hrb_ofc* h, int variant) {
     HRB_REQUIRE(h, "null handle");
-    HRB_REQUIRE(variant == 0 || variant == 1, "variant must be 0 (automatic) or 1 (generic kernel only)");
+    HRB_REQUIRE(variant == 0 || variant == 1, "variant must be 0 (automatic) or 1 (generic kernels only)");
     h->searchVariant = variant;
+    h->warpVariant = variant;
     return HRB_OK;
 }
 

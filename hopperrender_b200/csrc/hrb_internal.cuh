@@ -52,6 +52,9 @@ struct SearchArgs {
     const uint32_t* plane1;  // search plane of frame N-1 (m_inputFrameArray[1]): {Y,U,V,0} per luma pixel
     const uint32_t* plane2;  // search plane of frame N   (m_inputFrameArray[2])
     int pitch;               // words per search-plane row
+    const uint32_t* planeT1; // the same planes transposed ([x][y]); X steps read these
+    const uint32_t* planeT2;
+    int pitchT;              // words per transposed row (>= H)
     int W, H;                // frame size
     int lw, lh;              // flow size
     int rs;                  // resolution scalar
@@ -129,12 +132,15 @@ struct hrb_ofc {
     uint8_t* inputFrameArray[3];   // raw NV12 / P010 frames, rotated like m_inputFrameArray
     uint32_t* searchPlane[3];      // packed 8-bit search representation of the same slot
     int planePitch;                // words
+    uint32_t* searchPlaneT[3];     // transposed copy of searchPlane (X steps read these so that their accesses are row segments too)
+    int planePitchT;               // words
     uint8_t* outputFrameArray;
     int16_t* levelOffsets[2][2];   // [iteration parity][axis] window-level offsets
     size_t levelCapacity;          // entries per level array
     uint32_t* winSums;
     int16_t* offsetArrayScratch;   // [2][lh][lw], materialised on demand for taps
     int16_t* blurredOffsetArray[2];
+    uint32_t* flowMaxDev[2];       // max |value| of blurredOffsetArray[i] (rotates with it): lets warpFrames skip the mirror in the interior
     uint32_t* rawDeltaDev;
     // final level geometry after the last calculate (input of blur / offset tap)
     int lastIterParity, lastNWx, lastNWy, lastWs;
@@ -142,6 +148,8 @@ struct hrb_ofc {
 
     // taps / profiling
     int searchVariant;  // 0: automatic kernel selection, 1: generic sadPassKernel for every pass (A/B and parity tests)
+    int warpVariant;    // 0: automatic (table-driven fast kernel for modes 0-2), 1: generic warpFrameKernel for every mode
+    int smCount;
     bool tapMode;
     std::vector<hrb::PassTapDev> taps;
     hrb::Profile prof;
@@ -157,7 +165,7 @@ int launchWarpFrame(hrb_ofc* h, float t, int mode);
 int launchSearchPass(hrb_ofc* h, const SearchArgs& a, int R, int step);
 // kernels_search_big.cu: HRB_OK, an error code, or -1 when this (R, geometry) is not covered
 int launchSearchPassBig(hrb_ofc* h, const SearchArgs& a, int R, int step);
-int launchBlurFlow(hrb_ofc* h, const int16_t* lvlX, const int16_t* lvlY, int nWx, int wsLog2, int16_t* out);
+int launchBlurFlow(hrb_ofc* h, const int16_t* lvlX, const int16_t* lvlY, int nWx, int wsLog2, int16_t* out, uint32_t* flowMax);
 int launchExpandOffsets(hrb_ofc* h, const int16_t* lvlX, int nWxX, int wsLog2X, const int16_t* lvlY, int nWxY, int wsLog2Y,
                         int16_t* out);
 int microbenchSad(int device, double* gigaAbsdiffPerSec);

@@ -17,11 +17,13 @@ namespace hrb {
 namespace {
 
 // ------------------------------------------------------------------------------------------------
-// The SAD pass.  CTA = 8 warps over a TILE x TILE block of flow pixels; a warp owns 4 consecutive rows,
-// a lane one column.  R and STEP are compile-time so the candidate displacements are immediates.
+// The generic SAD pass (any window size, any resolution scalar).  CTA = 8 warps over a TILE x TILE block of
+// flow pixels in (u, v) coordinates (see View); a warp owns 4 consecutive v, a lane one u.  R is compile-time
+// so the candidate displacements fold into the address arithmetic.
 // ------------------------------------------------------------------------------------------------
 template <int R, int STEP> __global__ void __launch_bounds__(256) sadPassKernel(const SearchArgs a) {
     __shared__ uint32_t s_sums[16][16];  // [window inside the tile][layer]
+    const View<STEP> vw(a);
     const int lane = threadIdx.x, warp = threadIdx.y;
     const int tid = warp * 32 + lane;
     const int ws = a.ws;
@@ -30,51 +32,40 @@ template <int R, int STEP> __global__ void __launch_bounds__(256) sadPassKernel(
         s_sums[tid >> 4][tid & 15] = 0;
         __syncthreads();
     }
-    const int cx = blockIdx.x * TILE + lane;
+    const int cu = blockIdx.x * TILE + lane;
     const int rowBase = blockIdx.y * TILE + warp * 4;
     const int gh = ws < 4 ? ws : 4;  // rows of one accumulation group (inside one window row)
     constexpr int LO = candOffset<R>(0), HI = candOffset<R>(R - 1);
 
     for (int g = 0; g < 4; g += gh) {
-        const int cy0 = rowBase + g;
-        const int wx = cx >> a.wsLog2, wy = cy0 >> a.wsLog2;
-        const bool pixOk = cx < a.lw && cy0 < a.lh;                          // this lane has pixels to accumulate
-        const bool winOk = (wx << a.wsLog2) < a.lw && cy0 < a.lh;            // this lane's window exists (it may finalize a slice of it)
+        const int cv0 = rowBase + g;
+        const int wu = cu >> a.wsLog2, wv = cv0 >> a.wsLog2;
+        const int wx = View<STEP>::wx(wu, wv), wy = View<STEP>::wy(wu, wv);
+        const bool pixOk = cu < vw.lu && cv0 < vw.lv;                 // this lane has pixels to accumulate
+        const bool winOk = (wu << a.wsLog2) < vw.lu && cv0 < vw.lv;   // this lane's window exists (it may finalize a slice of it)
         uint32_t acc[16];
 #pragma unroll
         for (int z = 0; z < 16; ++z) acc[z] = 0;
         int ox = 0, oy = 0;
         if (winOk) loadWindowOffsets<STEP>(a, wx, wy, ox, oy);
         if (pixOk) {
-            const int sx = cx << a.rs;
+            const int su = cu << a.rs;
+            const int ou = View<STEP>::ou(ox, oy), ov = View<STEP>::ov(ox, oy);
+            const uint32_t* __restrict__ col = vw.p1 + mirrorSearch(su + ou, vw.dimU);
             for (int r = 0; r < gh; ++r) {
-                const int cy = cy0 + r;
-                if (cy >= a.lh) break;
-                const int sy = cy << a.rs;
-                const uint32_t f2 = __ldg(a.plane2 + (size_t)sy * a.pitch + sx);
-                if (STEP == 0) {
-                    const uint32_t* __restrict__ row = a.plane1 + (size_t)mirrorSearch(sy + oy, a.H) * a.pitch;
-                    const int bx = sx + ox;
-                    if (bx + LO >= 0 && bx + HI < a.W) {
-                        const uint32_t* __restrict__ p = row + bx;
+                const int cv = cv0 + r;
+                if (cv >= vw.lv) break;
+                const int sv = cv << a.rs;
+                const uint32_t f2 = __ldg(rowPtr(vw.p2 + su, vw.pitch, sv));
+                const int bv = sv + ov;
+                if (bv + LO >= 0 && bv + HI < vw.dimV) {
+                    const uint32_t* __restrict__ p = rowPtr(col, vw.pitch, bv);
 #pragma unroll
-                        for (int z = 0; z < R; ++z) acc[z] = sad4(__ldg(p + candOffset<R>(z)), f2, acc[z]);
-                    } else {
-#pragma unroll
-                        for (int z = 0; z < R; ++z) acc[z] = sad4(__ldg(row + mirrorSearch(bx + candOffset<R>(z), a.W)), f2, acc[z]);
-                    }
+                    for (int z = 0; z < R; ++z) acc[z] = sad4(__ldg(rowPtr(p, vw.pitch, candOffset<R>(z))), f2, acc[z]);
                 } else {
-                    const uint32_t* __restrict__ col = a.plane1 + mirrorSearch(sx + ox, a.W);
-                    const int by = sy + oy;
-                    if (by + LO >= 0 && by + HI < a.H) {
-                        const uint32_t* __restrict__ p = col + (size_t)by * a.pitch;
 #pragma unroll
-                        for (int z = 0; z < R; ++z) acc[z] = sad4(__ldg(p + (ptrdiff_t)candOffset<R>(z) * a.pitch), f2, acc[z]);
-                    } else {
-#pragma unroll
-                        for (int z = 0; z < R; ++z)
-                            acc[z] = sad4(__ldg(col + (size_t)mirrorSearch(by + candOffset<R>(z), a.H) * a.pitch), f2, acc[z]);
-                    }
+                    for (int z = 0; z < R; ++z)
+                        acc[z] = sad4(__ldg(rowPtr(col, vw.pitch, mirrorSearch(bv + candOffset<R>(z), vw.dimV))), f2, acc[z]);
                 }
             }
         }
@@ -114,7 +105,7 @@ template <int R, int STEP> __global__ void __launch_bounds__(256) sadPassKernel(
             bfly<4>(acc, 4, b2);
             int z0 = (b0 ? 8 : 0) + (b1 ? 4 : 0) + (b2 ? 2 : 0);
             int lwin = 0;
-            if (ws <= TILE) lwin = ((cy0 - blockIdx.y * TILE) >> a.wsLog2) * (TILE >> a.wsLog2) + (lane >> a.wsLog2);
+            if (ws <= TILE) lwin = ((cv0 - blockIdx.y * TILE) >> a.wsLog2) * (TILE >> a.wsLog2) + (lane >> a.wsLog2);
             if (ws == 8) {
                 atomicAdd(&s_sums[lwin][z0], acc[0]);
                 atomicAdd(&s_sums[lwin][z0 + 1], acc[1]);
@@ -136,13 +127,14 @@ template <int R, int STEP> __global__ void __launch_bounds__(256) sadPassKernel(
         if (ws <= TILE) {
             const int perEdge = TILE >> a.wsLog2;
             if (tid < perEdge * perEdge) {
-                const int wx = blockIdx.x * perEdge + (tid % perEdge);
-                const int wy = blockIdx.y * perEdge + (tid / perEdge);
+                const int wu = blockIdx.x * perEdge + (tid % perEdge);
+                const int wv = blockIdx.y * perEdge + (tid / perEdge);
+                const int wx = View<STEP>::wx(wu, wv), wy = View<STEP>::wy(wu, wv);
                 if (wx < a.nWx && wy < a.nWy) finalizeWindow<R, STEP>(a, wx, wy, s_sums[tid]);
             }
         } else if (tid < R) {
-            const int wx = (blockIdx.x * TILE) >> a.wsLog2, wy = (blockIdx.y * TILE) >> a.wsLog2;
-            atomicAdd(&a.winSums[(size_t)(wy * a.nWx + wx) * 16 + tid], s_sums[0][tid]);
+            const int wu = (blockIdx.x * TILE) >> a.wsLog2, wv = (blockIdx.y * TILE) >> a.wsLog2;
+            atomicAdd(&a.winSums[(size_t)(View<STEP>::wy(wu, wv) * a.nWx + View<STEP>::wx(wu, wv)) * 16 + tid], s_sums[0][tid]);
         }
     }
 }
@@ -159,7 +151,8 @@ template <int R, int STEP> __global__ void __launch_bounds__(128) finalizeLargeK
 
 template <int R> int launchPassR(hrb_ofc* h, const SearchArgs& a, int step, unsigned* launches) {
     const dim3 block(32, 8, 1);
-    const dim3 grid((a.lw + TILE - 1) / TILE, (a.lh + TILE - 1) / TILE, 1);
+    const int lu = step == 1 ? a.lw : a.lh, lv = step == 1 ? a.lh : a.lw;  // X steps run on the transposed planes (View)
+    const dim3 grid((lu + TILE - 1) / TILE, (lv + TILE - 1) / TILE, 1);
     const bool large = a.ws > TILE;
     if (large) HRB_CUDA(cudaMemsetAsync(a.winSums, 0, (size_t)a.nWx * a.nWy * 16 * sizeof(uint32_t), h->stream));
     bool done = false;
@@ -202,7 +195,7 @@ constexpr int BT = 32;          // outputs per tile edge
 constexpr int BIN = BT + 7;     // input rows / columns a tile needs
 
 __global__ void __launch_bounds__(256) blurFlowKernel(const int16_t* __restrict__ lvlX, const int16_t* __restrict__ lvlY, int nWx, int wsLog2,
-                                                     int16_t* __restrict__ out, int lw, int lh) {
+                                                     int16_t* __restrict__ out, int lw, int lh, uint32_t* __restrict__ flowMax) {
     __shared__ int16_t s_in[BIN][BIN + 1];
     __shared__ int s_h[BIN][BT];
     const int16_t* __restrict__ lvl = blockIdx.z == 0 ? lvlX : lvlY;
@@ -224,17 +217,23 @@ __global__ void __launch_bounds__(256) blurFlowKernel(const int16_t* __restrict_
     }
     __syncthreads();
     const int x = X0 + threadIdx.x;
-    if (x >= lw) return;
+    int peak = 0;  // largest |flow| this thread wrote: bounds every displacement warpFrames can apply
+    if (x < lw) {
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-        const int ly = threadIdx.y * 4 + j;
-        const int y = Y0 + ly;
-        if (y >= lh) break;
-        int s = 0;
+        for (int j = 0; j < 4; ++j) {
+            const int ly = threadIdx.y * 4 + j;
+            const int y = Y0 + ly;
+            if (y >= lh) break;
+            int s = 0;
 #pragma unroll
-        for (int k = 0; k < 8; ++k) s += s_h[ly + k][threadIdx.x];
-        out[(size_t)blockIdx.z * lw * lh + (size_t)y * lw + x] = (int16_t)(s / 64);
+            for (int k = 0; k < 8; ++k) s += s_h[ly + k][threadIdx.x];
+            const int v = s / 64;
+            out[(size_t)blockIdx.z * lw * lh + (size_t)y * lw + x] = (int16_t)v;
+            peak = max(peak, abs(v));
+        }
     }
+    peak = __reduce_max_sync(0xffffffffu, peak);
+    if (threadIdx.x == 0 && (uint32_t)peak > *reinterpret_cast<volatile uint32_t*>(flowMax)) atomicMax(flowMax, (uint32_t)peak);
 }
 
 // per-pixel offsetArray [2][lh][lw] from window-level arrays (test taps only)
@@ -281,11 +280,12 @@ int launchSearchPass(hrb_ofc* h, const SearchArgs& a, int R, int step) {
     return rc;
 }
 
-int launchBlurFlow(hrb_ofc* h, const int16_t* lvlX, const int16_t* lvlY, int nWx, int wsLog2, int16_t* out) {
+int launchBlurFlow(hrb_ofc* h, const int16_t* lvlX, const int16_t* lvlY, int nWx, int wsLog2, int16_t* out, uint32_t* flowMax) {
     const dim3 block(32, 8, 1);
     const dim3 grid((h->flowWidth + BT - 1) / BT, (h->flowHeight + BT - 1) / BT, 2);
+    HRB_CUDA(cudaMemsetAsync(flowMax, 0, sizeof(uint32_t), h->stream));
     profBegin(h, CLS_BLUR);
-    blurFlowKernel<<<grid, block, 0, h->stream>>>(lvlX, lvlY, nWx, wsLog2, out, h->flowWidth, h->flowHeight);
+    blurFlowKernel<<<grid, block, 0, h->stream>>>(lvlX, lvlY, nWx, wsLog2, out, h->flowWidth, h->flowHeight, flowMax);
     HRB_LAUNCH_CHECK();
     profEnd(h, CLS_BLUR, 1);
     return HRB_OK;

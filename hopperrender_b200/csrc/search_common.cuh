@@ -28,6 +28,35 @@ __device__ __forceinline__ uint32_t sad4(uint32_t a, uint32_t b, uint32_t c) {
     return d;
 }
 
+// A pass seen along its candidate axis: v is the axis the candidates move along and the row index of the plane in
+// use, u the contiguous axis (one lane per u).  Y steps read the row-major search planes (u = x, v = y); X steps read
+// the TRANSPOSED planes (u = y, v = x).  Both steps therefore run the same code and every warp access is a
+// contiguous row segment.  Window bookkeeping (offset arrays, biases) stays in (x, y).
+template <int STEP> struct View {
+    const uint32_t* __restrict__ p1;
+    const uint32_t* __restrict__ p2;
+    int pitch, dimU, dimV, lu, lv;
+    __device__ __forceinline__ explicit View(const SearchArgs& a) {
+        if (STEP == 1) {
+            p1 = a.plane1; p2 = a.plane2; pitch = a.pitch; dimU = a.W; dimV = a.H; lu = a.lw; lv = a.lh;
+        } else {
+            p1 = a.planeT1; p2 = a.planeT2; pitch = a.pitchT; dimU = a.H; dimV = a.W; lu = a.lh; lv = a.lw;
+        }
+    }
+    static __device__ __forceinline__ int wx(int wu, int wv) { return STEP == 1 ? wu : wv; }
+    static __device__ __forceinline__ int wy(int wu, int wv) { return STEP == 1 ? wv : wu; }
+    static __device__ __forceinline__ int ou(int ox, int oy) { return STEP == 1 ? ox : oy; }
+    static __device__ __forceinline__ int ov(int ox, int oy) { return STEP == 1 ? oy : ox; }
+};
+
+// base + rows * pitch (in words) as ONE IMAD.WIDE on the FMA pipe: keeps the per-fetch address arithmetic off the
+// ALU pipe, which the VABSDIFF4 stream saturates (nvcc otherwise emits 4-5 ALU instructions per row-strided fetch).
+__device__ __forceinline__ const uint32_t* rowPtr(const uint32_t* base, int pitchWords, int rows) {
+    unsigned long long r;
+    asm("mad.wide.s32 %0, %1, %2, %3;" : "=l"(r) : "r"(pitchWords), "r"(rows * 4), "l"((unsigned long long)base));
+    return reinterpret_cast<const uint32_t*>(r);
+}
+
 struct WindowCtx {
     int o;          // current offset of the window along the axis of this step
     uint32_t nw;    // in-range flow pixels of the window

@@ -57,16 +57,19 @@ def _smooth_flow(lh, lw, rng, amp):
 
 
 @pytest.mark.parametrize("hdr", [False, True])
-@pytest.mark.parametrize("mode", [0, 1, 2, 3, 4, 5, 6])
-@pytest.mark.parametrize("W,H,maxres,inS,outS", [(64, 48, 270, 0, 0), (130, 70, 35, 136, 144), (256, 144, 36, 0, 320), (320, 176, 22, 0, 0)])
-def test_warp_modes(synth, hdr, mode, W, H, maxres, inS, outS):
+@pytest.mark.parametrize("mode,variant", [(0, 0), (1, 0), (2, 0), (0, 1), (1, 1), (2, 1), (3, 0), (4, 0), (5, 0), (6, 0)])
+@pytest.mark.parametrize("W,H,maxres,inS,outS", [(64, 48, 270, 0, 0), (130, 70, 35, 136, 144), (256, 144, 36, 0, 320), (320, 176, 22, 0, 0),
+                                                 (200, 120, 270, 200, 204)])
+def test_warp_modes(synth, hdr, mode, variant, W, H, maxres, inS, outS):
+    """All seven output modes; modes 0-2 through both the table-driven fast kernel (variant 0) and the generic one (1)."""
     g, o = make_pair(hdr, H, W, inS, outS, black=4.0, white=250.0, maxres=maxres)
+    g.setSearchVariant(variant)
     for fr in frames(synth, W, H, hdr, 3, inS or None):
         g.updateFrame(fr)
         o.updateFrame(fr)
     lh, lw = g.m_opticalFlowFrameHeight, g.m_opticalFlowFrameWidth
     rng = np.random.default_rng(W * 7 + mode)
-    for amp, t in [(0, 0.5), (9, 0.0), (9, 1.0 / 6.0), (40, 0.4), (300, 0.5), (9, 1.0)]:
+    for amp, t in [(0, 0.5), (9, 0.0), (9, 1.0 / 6.0), (40, 0.4), (300, 0.5), (9, 1.0), (2000, 0.3)]:
         fl = _smooth_flow(lh, lw, rng, amp)
         g.writeFlow(fl)
         o.writeFlow(fl)
@@ -106,13 +109,19 @@ SEARCH_CASES = [
     (False, 320, 200, 270, 0, 9, "ramp"),
     (True, 384, 224, 270, 0, 16, "scene"),
     (False, 16, 16, 270, 0, 5, "random"),
+    (False, 722, 430, 430, 0, 16, "scene"),     # partial 32x32 tiles on both edges, windows 512..2
+    (True, 640, 384, 384, 672, 7, "scene"),
+    (False, 450, 258, 258, 0, 12, "random"),    # large offsets: mirrored halos in the sliding-window kernels
 ]
 
 
+@pytest.mark.parametrize("variant", [0, 1], ids=["auto", "generic"])
 @pytest.mark.parametrize("hdr,W,H,maxres,inS,R,kind", SEARCH_CASES)
-def test_search_ladder_taps(synth, hdr, W, H, maxres, inS, R, kind):
-    """Every pass of the ladder: window sums, arg-min layers and offsets are bit-exact."""
+def test_search_ladder_taps(synth, hdr, W, H, maxres, inS, R, kind, variant):
+    """Every pass of the ladder: window sums, arg-min layers and offsets are bit-exact — with the automatic kernel
+    selection (sliding-window kernels for windows >= 32) and with the generic kernel forced for every pass."""
     g, o = make_pair(hdr, H, W, inS, 0, maxres=maxres, R=R)
+    g.setSearchVariant(variant)
     g.setTapMode(True)
     o.enableTaps(True)
     for fr in frames(synth, W, H, hdr, 3, inS or None, kind):
@@ -316,3 +325,34 @@ def test_cpp_shim_replay_matches_python_replay_over_the_oracle(synth, hdr, tmp_p
         assert int(g_line[3]) == int(info["warped"])
         assert int(g_line[5], 16) == crc, f"delivered frame {g_line[:2]} differs"
     assert any(not i["warped"] and i["source"] >= 3 for i, _ in exp), "the scene cut should have forced a copyFrame"
+
+
+@pytest.mark.parametrize("black,white", [(0.0, 255.0), (16.0, 235.0), (3.5, 200.25), (0.0, 1.0), (100.0, 101.0), (250.0, 5.0)])
+def test_levels_exhaustive(black, white):
+    """Level correction for every 16-bit (P010 container) and 8-bit input value, luma and chroma, against the oracle's
+    IEEE division — pins the hoisted-reciprocal division of the CUDA kernels (copy, warp) to correctly rounded results."""
+    for hdr in (True, False):
+        W, H = 512, 128 if hdr else 16
+        g, o = make_pair(hdr, H, W, black=black, white=white)
+        dt = np.uint16 if hdr else np.uint8
+        nvals = 65536 if hdr else 256
+        fr = np.zeros((H + H // 2) * W, dt)
+        fr[:H * W] = np.arange(H * W) % nvals            # every value in the luma plane ...
+        fr[H * W:] = (np.arange(H * W // 2) * 2 + np.arange(H * W // 2) % 2) % nvals  # ... and in both chroma channels
+        if hdr:
+            assert H * W >= nvals and H * W // 2 >= nvals // 2
+        for _ in range(3):
+            g.updateFrame(fr)
+            o.updateFrame(fr)
+        a, b = out_array(g, hdr), out_array(o, hdr)
+        g.copyFrame()
+        o.copyFrame()
+        g.downloadFrame(a)
+        o.downloadFrame(b)
+        assert np.array_equal(a, b), f"copyFrame hdr={hdr}: {np.count_nonzero(a != b)} differ"
+        # zero flow, identical frames: warp mode 2 blends each sample with itself -> levels applied to every interior value
+        g.warpFrames(0.5, 2)
+        o.warpFrames(0.5, 2)
+        g.downloadFrame(a)
+        o.downloadFrame(b)
+        assert np.array_equal(a, b), f"warpFrames hdr={hdr}: {np.count_nonzero(a != b)} differ"
