@@ -20,7 +20,8 @@ streams = shard.assign_streams(5, world, rank)
 shard.barrier()
 frames, ms, launches = shard.combine(frames_local=600 * len(streams), ms_local=100.0 + 50.0 * rank, launches_local=10 + rank)
 fps = shard.throughput(600 * len(streams), 100.0 + 50.0 * rank)
-print(json.dumps({"rank": rank, "streams": streams, "frames": frames, "ms": ms, "launches": launches, "fps": fps}), flush=True)
+with open(os.path.join(os.environ["HRB_TEST_OUT"], f"rank{rank}.json"), "w") as f:
+    json.dump({"rank": rank, "streams": streams, "frames": frames, "ms": ms, "launches": launches, "fps": fps}, f)
 dist.destroy_process_group()
 """ % ROOT
 
@@ -37,12 +38,11 @@ def test_stream_assignment_covers_every_stream_once():
 def test_two_ranks_combine_over_gloo(tmp_path):
     script = tmp_path / "worker.py"
     script.write_text(WORKER)
-    env = dict(os.environ, MASTER_ADDR="127.0.0.1", MASTER_PORT="29617", OMP_NUM_THREADS="1")
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1", MASTER_PORT="29617", OMP_NUM_THREADS="1", HRB_TEST_OUT=str(tmp_path))
     res = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
                           "--master-port", "29617", str(script)], capture_output=True, text=True, timeout=240, env=env, cwd=ROOT)
     assert res.returncode == 0, res.stderr[-2000:]
-    rows = [json.loads(ln) for ln in res.stdout.splitlines() if ln.startswith("{")]
-    assert len(rows) == 2
+    rows = [json.load(open(tmp_path / f"rank{r}.json")) for r in range(2)]
     for r in rows:
         assert r["frames"] == 600 * 5            # 3 + 2 streams
         assert r["ms"] == 150.0                  # the slower rank
