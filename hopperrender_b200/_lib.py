@@ -57,7 +57,10 @@ PROTOTYPES = {
     "hrb_ofc_reset": (C.c_int, [_P]),
     "hrb_ofc_update_frame_device": (C.c_int, [_P, _P]),
     "hrb_ofc_output_device_ptr": (C.c_int, [_P, C.POINTER(_P)]),
-    "hrb_ofc_download_frame_async": (C.c_int, [_P, _P]),
+    "hrb_ofc_update_frame_async": (C.c_int, [_P, _P]),
+    "hrb_ofc_wait_upload": (C.c_int, [_P]),
+    "hrb_ofc_download_frame_async": (C.c_int, [_P, _P, C.POINTER(C.c_ulonglong)]),
+    "hrb_ofc_wait_download": (C.c_int, [_P, C.c_ulonglong]),
     "hrb_ofc_calculate_optical_flow_async": (C.c_int, [_P]),
     "hrb_ofc_synchronize": (C.c_int, [_P]),
     "hrb_ofc_stream": (C.c_int, [_P, C.POINTER(_P)]),

@@ -266,24 +266,27 @@ static int enqueueFlow(hrb_ofc* h) {
 }
 
 static int finishUpdate(hrb_ofc* h) {
-    // rotate: [0] <- [1] <- [2] <- new (opticalFlowCalcSDR.cpp:22-26)
-    uint8_t* f0 = h->inputFrameArray[0];
-    h->inputFrameArray[0] = h->inputFrameArray[1];
-    h->inputFrameArray[1] = h->inputFrameArray[2];
-    h->inputFrameArray[2] = f0;
-    uint32_t* p0 = h->searchPlane[0];
-    h->searchPlane[0] = h->searchPlane[1];
-    h->searchPlane[1] = h->searchPlane[2];
-    h->searchPlane[2] = p0;
-    uint32_t* t0 = h->searchPlaneT[0];
-    h->searchPlaneT[0] = h->searchPlaneT[1];
-    h->searchPlaneT[1] = h->searchPlaneT[2];
-    h->searchPlaneT[2] = t0;
+    // the new frame sits in slot [3]; rotate [0] <- [1] <- [2] <- [3], the old [0] becomes the next upload target
+    // (same result as the reference's write-into-[0]-then-rotate, opticalFlowCalcSDR.cpp:20-26)
+    auto rot = [](auto** v) {
+        auto* f0 = v[0];
+        v[0] = v[1];
+        v[1] = v[2];
+        v[2] = v[3];
+        v[3] = f0;
+    };
+    rot(h->inputFrameArray);
+    rot(h->searchPlane);
+    rot(h->searchPlaneT);
     h->frameCount++;
+    // every reader of the buffer that just became slot [3] (the warps of the previous source frame) is already enqueued
+    HRB_CUDA(cudaEventRecord(h->spareFreeEvent, h->stream));
     return launchPackFrame(h, 2);
 }
 
-static int beginUpdate(hrb_ofc* h) {
+// `onStream`: the stream the frame copy will be enqueued on; the flow timer starts there (m_ofcStartedEvent is the
+// upload event in the reference, opticalFlowCalcSDR.cpp:20)
+static int beginUpdate(hrb_ofc* h, cudaStream_t onStream) {
     HRB_CUDA(cudaSetDevice(h->device));
     h->curRec = (h->curRec + 1) % hrb_ofc::kFlowRecords;
     hrb_ofc::FlowRecord& rec = h->flowRec[h->curRec];
@@ -291,8 +294,45 @@ static int beginUpdate(hrb_ofc* h) {
         const int rc = resolveRecord(h, rec);
         if (rc) return rc;
     }
-    HRB_CUDA(cudaEventRecord(rec.start, h->stream));  // m_ofcStartedEvent, opticalFlowCalcSDR.cpp:20
+    if (onStream != h->stream) HRB_CUDA(cudaStreamWaitEvent(onStream, h->spareFreeEvent, 0));
+    HRB_CUDA(cudaEventRecord(rec.start, onStream));
     rec.startValid = true;
+    return HRB_OK;
+}
+
+static int uploadFrame(hrb_ofc* h, const uint8_t* input_planes, bool wait) {
+    int rc = beginUpdate(h, h->upStream);
+    if (rc) return rc;
+    // write into the upload slot on the upload stream (opticalFlowCalcSDR.cpp:20), then hand it to the compute stream
+    HRB_CUDA(cudaMemcpyAsync(h->inputFrameArray[3], input_planes, h->inFrameBytes, cudaMemcpyHostToDevice, h->upStream));
+    HRB_CUDA(cudaEventRecord(h->uploadDoneEvent, h->upStream));
+    HRB_CUDA(cudaStreamWaitEvent(h->stream, h->uploadDoneEvent, 0));
+    rc = finishUpdate(h);
+    if (rc) return rc;
+    if (wait) HRB_CUDA(cudaEventSynchronize(h->uploadDoneEvent));  // the caller's buffer is free again; everything else continues asynchronously
+    return HRB_OK;
+}
+
+static int enqueueDownload(hrb_ofc* h, uint8_t* dst, unsigned long long* ticket) {
+    HRB_CUDA(cudaSetDevice(h->device));
+    const int slot = h->outCur;
+    HRB_CUDA(cudaStreamWaitEvent(h->downStream, h->outReady[slot], 0));
+    HRB_CUDA(cudaMemcpyAsync(dst, h->outputRing[slot], h->outFrameBytes, cudaMemcpyDeviceToHost, h->downStream));
+    HRB_CUDA(cudaEventRecord(h->outFree[slot], h->downStream));
+    const unsigned long long seq = ++h->downloadSeq;
+    HRB_CUDA(cudaEventRecord(h->ticketEvent[seq % hrb_ofc::kTickets], h->downStream));
+    if (ticket) *ticket = seq;
+    h->outCur = (slot + 1) % hrb_ofc::kOutRing;
+    return HRB_OK;
+}
+
+// warpFrames / copyFrame are about to overwrite ring slot outCur: its previous download must have finished
+static int beginOutput(hrb_ofc* h) {
+    HRB_CUDA(cudaSetDevice(h->device));
+    HRB_CUDA(cudaStreamWaitEvent(h->stream, h->outFree[h->outCur], 0));
+    HRB_CUDA(cudaEventRecord(h->warpStartedEvent, h->stream));  // m_warpStartedEvent, opticalFlowCalcSDR.cpp:164
+    h->warpStartedValid = true;
+    h->outView = h->outCur;
     return HRB_OK;
 }
 
@@ -369,12 +409,20 @@ int hrb_ofc_create(hrb_ofc** out, const hrb_ofc_desc* d) {
     }
     h->lastIterParity = 0;
     h->lastNWx = h->lastNWy = h->lastWs = 0;
-    for (int i = 0; i < 3; ++i) {
+    for (int i = 0; i < 4; ++i) {
         h->inputFrameArray[i] = nullptr;
         h->searchPlane[i] = nullptr;
         h->searchPlaneT[i] = nullptr;
     }
-    h->outputFrameArray = nullptr;
+    for (int i = 0; i < hrb_ofc::kOutRing; ++i) {
+        h->outputRing[i] = nullptr;
+        h->outReady[i] = h->outFree[i] = nullptr;
+    }
+    for (auto& e : h->ticketEvent) e = nullptr;
+    h->upStream = h->downStream = nullptr;
+    h->spareFreeEvent = nullptr;
+    h->outCur = h->outView = 0;
+    h->downloadSeq = 0;
     h->levelOffsets[0][0] = h->levelOffsets[0][1] = h->levelOffsets[1][0] = h->levelOffsets[1][1] = nullptr;
     h->winSums = nullptr;
     h->offsetArrayScratch = nullptr;
@@ -405,7 +453,7 @@ int hrb_ofc_create(hrb_ofc** out, const hrb_ofc_desc* d) {
     const size_t planeTBytes = (size_t)h->planePitchT * h->frameWidth * sizeof(uint32_t);
     h->levelCapacity = ((lw + 1) / 2) * ((lh + 1) / 2);
     const size_t winSumEntries = ((lw + 63) / 64) * ((lh + 63) / 64) * 16 + 16;
-    const size_t need = 3 * (h->inFrameBytes + planeBytes + planeTBytes) + h->outFrameBytes + 4 * h->levelCapacity * 2 + winSumEntries * 4 + 3 * 2 * lw * lh * 2;
+    const size_t need = 4 * (h->inFrameBytes + planeBytes + planeTBytes) + 3 * h->outFrameBytes + 4 * h->levelCapacity * 2 + winSumEntries * 4 + 3 * 2 * lw * lh * 2;
 
     // replaces detectDevices' memory check (opticalFlowCalc.cpp:48-51,86-96)
     size_t freeB = 0, totalB = 0;
@@ -442,8 +490,18 @@ int hrb_ofc_create(hrb_ofc** out, const hrb_ofc_desc* d) {
     }
     HRB_TRY(cudaEventCreate(&h->warpStartedEvent));
     HRB_TRY(cudaEventCreate(&h->warpEndEvent));
-    HRB_TRY(cudaEventCreateWithFlags(&h->uploadDoneEvent, cudaEventDisableTiming));
-    for (int i = 0; i < 3; ++i) {
+    HRB_TRY(cudaEventCreateWithFlags(&h->uploadDoneEvent, cudaEventBlockingSync | cudaEventDisableTiming));
+    HRB_TRY(cudaStreamCreateWithFlags(&h->upStream, cudaStreamNonBlocking));
+    HRB_TRY(cudaStreamCreateWithFlags(&h->downStream, cudaStreamNonBlocking));
+    HRB_TRY(cudaEventCreateWithFlags(&h->spareFreeEvent, cudaEventDisableTiming));
+    for (int i = 0; i < hrb_ofc::kOutRing; ++i) {
+        HRB_TRY(cudaEventCreateWithFlags(&h->outReady[i], cudaEventDisableTiming));
+        HRB_TRY(cudaEventCreate(&h->outFree[i]));
+        HRB_TRY(cudaMalloc(&h->outputRing[i], h->outFrameBytes));
+        HRB_TRY(cudaMemsetAsync(h->outputRing[i], 0, h->outFrameBytes, h->stream));
+    }
+    for (auto& e : h->ticketEvent) HRB_TRY(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    for (int i = 0; i < 4; ++i) {
         HRB_TRY(cudaMalloc(&h->inputFrameArray[i], h->inFrameBytes));
         HRB_TRY(cudaMemsetAsync(h->inputFrameArray[i], 0, h->inFrameBytes, h->stream));
         HRB_TRY(cudaMalloc(&h->searchPlane[i], planeBytes));
@@ -451,8 +509,6 @@ int hrb_ofc_create(hrb_ofc** out, const hrb_ofc_desc* d) {
         HRB_TRY(cudaMalloc(&h->searchPlaneT[i], planeTBytes));
         HRB_TRY(cudaMemsetAsync(h->searchPlaneT[i], 0, planeTBytes, h->stream));
     }
-    HRB_TRY(cudaMalloc(&h->outputFrameArray, h->outFrameBytes));
-    HRB_TRY(cudaMemsetAsync(h->outputFrameArray, 0, h->outFrameBytes, h->stream));
     for (int p = 0; p < 2; ++p)
         for (int ax = 0; ax < 2; ++ax) {
             HRB_TRY(cudaMalloc(&h->levelOffsets[p][ax], h->levelCapacity * sizeof(int16_t)));
@@ -478,18 +534,29 @@ void hrb_ofc_destroy(hrb_ofc* h) {
     if (!h) return;
     cudaSetDevice(h->device);
     if (h->stream) cudaStreamSynchronize(h->stream);  // clFinish, opticalFlowCalcSDR.cpp:186
+    if (h->upStream) cudaStreamSynchronize(h->upStream);
+    if (h->downStream) cudaStreamSynchronize(h->downStream);
     freeTaps(h);
     for (auto& p : h->prof.pending) {
         if (p.a) cudaEventDestroy(p.a);
         if (p.b) cudaEventDestroy(p.b);
     }
     for (auto e : h->prof.pool) cudaEventDestroy(e);
-    for (int i = 0; i < 3; ++i) {
+    for (int i = 0; i < 4; ++i) {
         cudaFree(h->inputFrameArray[i]);
         cudaFree(h->searchPlane[i]);
         cudaFree(h->searchPlaneT[i]);
     }
-    cudaFree(h->outputFrameArray);
+    for (int i = 0; i < hrb_ofc::kOutRing; ++i) {
+        cudaFree(h->outputRing[i]);
+        if (h->outReady[i]) cudaEventDestroy(h->outReady[i]);
+        if (h->outFree[i]) cudaEventDestroy(h->outFree[i]);
+    }
+    for (auto e : h->ticketEvent)
+        if (e) cudaEventDestroy(e);
+    if (h->spareFreeEvent) cudaEventDestroy(h->spareFreeEvent);
+    if (h->upStream) cudaStreamDestroy(h->upStream);
+    if (h->downStream) cudaStreamDestroy(h->downStream);
     for (int p = 0; p < 2; ++p)
         for (int ax = 0; ax < 2; ++ax) cudaFree(h->levelOffsets[p][ax]);
     cudaFree(h->winSums);
@@ -513,22 +580,26 @@ void hrb_ofc_destroy(hrb_ofc* h) {
 
 int hrb_ofc_update_frame(hrb_ofc* h, const uint8_t* input_planes) {
     HRB_REQUIRE(h && input_planes, "null argument");
-    int rc = beginUpdate(h);
-    if (rc) return rc;
-    // blocking write into m_inputFrameArray[0] (opticalFlowCalcSDR.cpp:20)
-    HRB_CUDA(cudaMemcpyAsync(h->inputFrameArray[0], input_planes, h->inFrameBytes, cudaMemcpyHostToDevice, h->stream));
-    HRB_CUDA(cudaEventRecord(h->uploadDoneEvent, h->stream));
-    rc = finishUpdate(h);
-    if (rc) return rc;
-    HRB_CUDA(cudaEventSynchronize(h->uploadDoneEvent));  // the caller's buffer is free again; packing continues asynchronously
+    return uploadFrame(h, input_planes, true);
+}
+
+int hrb_ofc_update_frame_async(hrb_ofc* h, const uint8_t* pinned_input_planes) {
+    HRB_REQUIRE(h && pinned_input_planes, "null argument");
+    return uploadFrame(h, pinned_input_planes, false);
+}
+
+int hrb_ofc_wait_upload(hrb_ofc* h) {
+    HRB_REQUIRE(h, "null handle");
+    HRB_CUDA(cudaSetDevice(h->device));
+    HRB_CUDA(cudaEventSynchronize(h->uploadDoneEvent));
     return HRB_OK;
 }
 
 int hrb_ofc_update_frame_device(hrb_ofc* h, const void* device_planes) {
     HRB_REQUIRE(h && device_planes, "null argument");
-    int rc = beginUpdate(h);
+    int rc = beginUpdate(h, h->stream);
     if (rc) return rc;
-    HRB_CUDA(cudaMemcpyAsync(h->inputFrameArray[0], device_planes, h->inFrameBytes, cudaMemcpyDeviceToDevice, h->stream));
+    HRB_CUDA(cudaMemcpyAsync(h->inputFrameArray[3], device_planes, h->inFrameBytes, cudaMemcpyDeviceToDevice, h->stream));
     return finishUpdate(h);
 }
 
@@ -551,46 +622,59 @@ int hrb_ofc_warp_frames(hrb_ofc* h, float blending_scalar, int frame_output_mode
         return HRB_ERR_BLEND_RANGE;
     }
     HRB_REQUIRE(frame_output_mode >= 0 && frame_output_mode <= 6, "frame_output_mode outside 0..6");
-    HRB_CUDA(cudaSetDevice(h->device));
-    HRB_CUDA(cudaEventRecord(h->warpStartedEvent, h->stream));  // m_warpStartedEvent, opticalFlowCalcSDR.cpp:164
-    h->warpStartedValid = true;
-    return launchWarpFrame(h, blending_scalar, frame_output_mode);
+    int rc = beginOutput(h);
+    if (rc) return rc;
+    rc = launchWarpFrame(h, blending_scalar, frame_output_mode);
+    if (rc) return rc;
+    HRB_CUDA(cudaEventRecord(h->outReady[h->outCur], h->stream));
+    return HRB_OK;
 }
 
 int hrb_ofc_copy_frame(hrb_ofc* h) {
     HRB_REQUIRE(h, "null handle");
-    HRB_CUDA(cudaSetDevice(h->device));
     const int frameIndex = h->frameCount >= 3 ? 0 : h->frameCount >= 2 ? 1 : 2;  // opticalFlowCalcSDR.cpp:173
-    HRB_CUDA(cudaEventRecord(h->warpStartedEvent, h->stream));
-    h->warpStartedValid = true;
-    return launchCopyFrame(h, frameIndex);
+    int rc = beginOutput(h);
+    if (rc) return rc;
+    rc = launchCopyFrame(h, frameIndex);
+    if (rc) return rc;
+    HRB_CUDA(cudaEventRecord(h->outReady[h->outCur], h->stream));
+    return HRB_OK;
 }
 
 int hrb_ofc_download_frame(hrb_ofc* h, uint8_t* output_planes) {
     HRB_REQUIRE(h && output_planes, "null argument");
-    HRB_CUDA(cudaSetDevice(h->device));
-    HRB_CUDA(cudaMemcpyAsync(output_planes, h->outputFrameArray, h->outFrameBytes, cudaMemcpyDeviceToHost, h->stream));
-    HRB_CUDA(cudaEventRecord(h->warpEndEvent, h->stream));
-    HRB_CUDA(cudaEventSynchronize(h->warpEndEvent));
+    const int slot = h->outCur;
+    const int rc = enqueueDownload(h, output_planes, nullptr);
+    if (rc) return rc;
+    HRB_CUDA(cudaEventSynchronize(h->outFree[slot]));  // blocking read, opticalFlowCalcSDR.cpp:33
     if (h->warpStartedValid) {  // opticalFlowCalcSDR.cpp:36-41
         float ms = 0;
-        HRB_CUDA(cudaEventElapsedTime(&ms, h->warpStartedEvent, h->warpEndEvent));
+        HRB_CUDA(cudaEventElapsedTime(&ms, h->warpStartedEvent, h->outFree[slot]));
         h->warpCalcTime = (double)ms / 1e3;
     }
     return HRB_OK;
 }
 
-int hrb_ofc_download_frame_async(hrb_ofc* h, uint8_t* pinned_output_planes) {
+int hrb_ofc_download_frame_async(hrb_ofc* h, uint8_t* pinned_output_planes, unsigned long long* ticket) {
     HRB_REQUIRE(h && pinned_output_planes, "null argument");
+    return enqueueDownload(h, pinned_output_planes, ticket);
+}
+
+int hrb_ofc_wait_download(hrb_ofc* h, unsigned long long ticket) {
+    HRB_REQUIRE(h, "null handle");
+    HRB_REQUIRE(ticket >= 1 && ticket <= h->downloadSeq, "unknown ticket");
     HRB_CUDA(cudaSetDevice(h->device));
-    HRB_CUDA(cudaMemcpyAsync(pinned_output_planes, h->outputFrameArray, h->outFrameBytes, cudaMemcpyDeviceToHost, h->stream));
+    if (h->downloadSeq - ticket >= (unsigned long long)hrb_ofc::kTickets) return HRB_OK;  // its event was reused, i.e. it completed long ago
+    HRB_CUDA(cudaEventSynchronize(h->ticketEvent[ticket % hrb_ofc::kTickets]));
     return HRB_OK;
 }
 
 int hrb_ofc_synchronize(hrb_ofc* h) {
     HRB_REQUIRE(h, "null handle");
     HRB_CUDA(cudaSetDevice(h->device));
+    HRB_CUDA(cudaStreamSynchronize(h->upStream));
     HRB_CUDA(cudaStreamSynchronize(h->stream));
+    HRB_CUDA(cudaStreamSynchronize(h->downStream));
     return resolveFlow(h);
 }
 
@@ -602,7 +686,7 @@ int hrb_ofc_stream(hrb_ofc* h, void** out) {
 
 int hrb_ofc_output_device_ptr(hrb_ofc* h, void** out) {
     HRB_REQUIRE(h && out, "null argument");
-    *out = h->outputFrameArray;
+    *out = h->outputRing[h->outView];
     return HRB_OK;
 }
 
@@ -749,7 +833,7 @@ int hrb_ofc_read_buffer(hrb_ofc* h, int which, void* dst, size_t bytes) {
         HRB_CUDA(cudaMemcpyAsync(dst, h->blurredOffsetArray[which == HRB_BUF_FLOW_FOR_WARP ? 0 : 1], bytes, cudaMemcpyDeviceToHost, h->stream));
     } else if (which == HRB_BUF_OUTPUT_FRAME) {
         HRB_REQUIRE(bytes <= h->outFrameBytes, "size larger than the output frame");
-        HRB_CUDA(cudaMemcpyAsync(dst, h->outputFrameArray, bytes, cudaMemcpyDeviceToHost, h->stream));
+        HRB_CUDA(cudaMemcpyAsync(dst, h->outputRing[h->outView], bytes, cudaMemcpyDeviceToHost, h->stream));
     } else if (which == HRB_BUF_RAW_FRAME_DELTA) {
         HRB_REQUIRE(bytes == sizeof(uint32_t), "size must be 4");
         HRB_CUDA(cudaMemcpyAsync(dst, h->rawDeltaDev, bytes, cudaMemcpyDeviceToHost, h->stream));

@@ -126,15 +126,27 @@ struct hrb_ofc {
     int curRec;
     cudaEvent_t warpStartedEvent, warpEndEvent, uploadDoneEvent;
     bool warpStartedValid;
+    // transfers run on their own streams so that the upload of frame N+1 and the downloads of the outputs of frame N
+    // overlap the kernels: input slot [3] is the upload target (rotated in by updateFrame), the output is a ring of 3
+    cudaStream_t upStream, downStream;
+    cudaEvent_t spareFreeEvent;          // compute stream: last readers of the buffer that became input slot [3] are enqueued
+    static constexpr int kOutRing = 3;
+    cudaEvent_t outReady[kOutRing];      // compute stream: warp/copy into ring slot i finished
+    cudaEvent_t outFree[kOutRing];       // download stream: D2H of ring slot i finished
+    int outCur;                          // ring slot warpFrames / copyFrame write next (advances on download)
+    int outView;                         // ring slot written most recently
+    static constexpr int kTickets = 16;
+    cudaEvent_t ticketEvent[kTickets];
+    unsigned long long downloadSeq;      // downloads enqueued so far (ticket = sequence number, 1-based)
 
     // device arrays
     size_t inFrameBytes, outFrameBytes;
-    uint8_t* inputFrameArray[3];   // raw NV12 / P010 frames, rotated like m_inputFrameArray
-    uint32_t* searchPlane[3];      // packed 8-bit search representation of the same slot
+    uint8_t* inputFrameArray[4];   // raw NV12 / P010 frames, [0..2] rotated like m_inputFrameArray, [3] = upload target
+    uint32_t* searchPlane[4];      // packed 8-bit search representation of the same slot
     int planePitch;                // words
-    uint32_t* searchPlaneT[3];     // transposed copy of searchPlane (X steps read these so that their accesses are row segments too)
+    uint32_t* searchPlaneT[4];     // transposed copy of searchPlane (X steps read these so that their accesses are row segments too)
     int planePitchT;               // words
-    uint8_t* outputFrameArray;
+    uint8_t* outputRing[3];        // m_outputFrameArray, as a ring so that a download can overlap the next warp
     int16_t* levelOffsets[2][2];   // [iteration parity][axis] window-level offsets
     size_t levelCapacity;          // entries per level array
     uint32_t* winSums;
@@ -165,6 +177,8 @@ int launchWarpFrame(hrb_ofc* h, float t, int mode);
 int launchSearchPass(hrb_ofc* h, const SearchArgs& a, int R, int step);
 // kernels_search_big.cu: HRB_OK, an error code, or -1 when this (R, geometry) is not covered
 int launchSearchPassBig(hrb_ofc* h, const SearchArgs& a, int R, int step);
+// kernels_search_cand.cu: a whole pass for 2 <= ws <= 16 at full flow resolution; same return convention
+int launchSearchPassCand(hrb_ofc* h, const SearchArgs& a, int R, int step);
 int launchBlurFlow(hrb_ofc* h, const int16_t* lvlX, const int16_t* lvlY, int nWx, int wsLog2, int16_t* out, uint32_t* flowMax);
 int launchExpandOffsets(hrb_ofc* h, const int16_t* lvlX, int nWxX, int wsLog2X, const int16_t* lvlY, int nWxY, int wsLog2Y,
                         int16_t* out);

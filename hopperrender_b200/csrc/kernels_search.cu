@@ -156,6 +156,11 @@ template <int R> int launchPassR(hrb_ofc* h, const SearchArgs& a, int step, unsi
     const bool large = a.ws > TILE;
     if (large) HRB_CUDA(cudaMemsetAsync(a.winSums, 0, (size_t)a.nWx * a.nWy * 16 * sizeof(uint32_t), h->stream));
     bool done = false;
+    if (a.rs == 0 && a.ws <= 16 && h->searchVariant != 1) {  // staged small-window kernel (kernels_search_cand.cu)
+        const int rc = launchSearchPassCand(h, a, R, step);
+        if (rc > 0) return rc;
+        done = rc == HRB_OK;
+    }
     if (a.rs == 0 && a.ws >= 32 && h->searchVariant != 1) {  // sliding-window kernels (kernels_search_big.cu)
         const int rc = launchSearchPassBig(h, a, R, step);
         if (rc > 0) return rc;

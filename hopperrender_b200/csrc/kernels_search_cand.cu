@@ -1,0 +1,217 @@
+// kernels_search_cand.cu — search passes for the small windows (2, 4, 8, 16 flow pixels) at full flow resolution:
+// 4 of the 11 iterations at 4K, and the ones where every window has its own offset.
+//
+// The generic kernel fetches frame 1 once per pixel-candidate from global memory: one 64-bit address computation and
+// one L1 transaction per VABSDIFF4.  Here a CTA owns a 32 x 64 tile (u x v, see View) and first looks at the offsets
+// of all windows in the tile.  Motion fields are smooth, so they almost always span a few pixels only; the CTA then
+// stages the frame-1 region every candidate of every window of the tile can touch —
+//     (64 + (HI-LO) + spread_v) rows  x  (32 + spread_u) columns  (<= 192 x 48 words) —
+// in shared memory with 16-byte copies, after which a pixel-candidate costs one LDS with an IMMEDIATE offset (the
+// candidate displacement is a compile-time multiple of the row pitch) and one VABSDIFF4.  Tiles at the frame border
+// stage through the mirror; tiles whose offsets spread too far for the buffer fall back to global fetches.  The
+// reduction, arg-min and offset update are those of the generic kernel.
+#include <climits>
+
+#include "search_common.cuh"
+
+namespace hrb {
+
+namespace {
+
+constexpr int CT_U = 32, CT_V = 64;   // tile
+constexpr int SP = 52;                // staged row pitch in words (48 + alignment slack, 13 x 16 B)
+constexpr int RV_MAX = 192;           // staged rows
+constexpr int RU_MAX = 48;            // staged columns actually addressed
+
+template <int R, int STEP> __global__ void __launch_bounds__(256) sadCandKernel(const SearchArgs a) {
+    constexpr int LO = candOffset<R>(0), HI = candOffset<R>(R - 1), SPAN = HI - LO;
+    __shared__ __align__(16) uint32_t s_f1[RV_MAX * SP];
+    __shared__ uint32_t s_sums[32][16];  // [window inside the tile][layer] (ws 8: 4 x 8 windows, ws 16: 2 x 4)
+    __shared__ int s_off[512];           // per window of the tile: (ou & 0xffff) | (ov << 16)
+    __shared__ int s_rng[4];             // min ou, max ou, min ov, max ov
+
+    const View<STEP> vw(a);
+    const int lane = threadIdx.x, warp = threadIdx.y;
+    const int tid = warp * 32 + lane;
+    const int ws = a.ws, wsLog2 = a.wsLog2;
+    const int U0 = blockIdx.x * CT_U, V0 = blockIdx.y * CT_V;
+    const int nwu = CT_U >> wsLog2, nwv = CT_V >> wsLog2;  // windows of the tile along u, v
+
+    // ---- A. offsets of the tile's windows, and their range ------------------------------------------------------
+    if (tid < 4) s_rng[tid] = (tid & 1) ? INT_MIN : INT_MAX;
+    for (int i = tid; i < 32 * 16; i += 256) s_sums[0][i] = 0;
+    __syncthreads();
+    {
+        int mnU = INT_MAX, mxU = INT_MIN, mnV = INT_MAX, mxV = INT_MIN;
+        for (int i = tid; i < nwu * nwv; i += 256) {
+            const int lwu = i % nwu, lwv = i / nwu;
+            const int wu = (U0 >> wsLog2) + lwu, wv = (V0 >> wsLog2) + lwv;
+            int packed = 0;
+            if ((wu << wsLog2) < vw.lu && (wv << wsLog2) < vw.lv) {
+                int ox, oy;
+                loadWindowOffsets<STEP>(a, View<STEP>::wx(wu, wv), View<STEP>::wy(wu, wv), ox, oy);
+                const int ou = View<STEP>::ou(ox, oy), ov = View<STEP>::ov(ox, oy);
+                packed = (ou & 0xffff) | (ov << 16);
+                mnU = min(mnU, ou); mxU = max(mxU, ou); mnV = min(mnV, ov); mxV = max(mxV, ov);
+            }
+            s_off[i] = packed;
+        }
+        mnU = __reduce_min_sync(0xffffffffu, mnU); mxU = __reduce_max_sync(0xffffffffu, mxU);
+        mnV = __reduce_min_sync(0xffffffffu, mnV); mxV = __reduce_max_sync(0xffffffffu, mxV);
+        if (lane == 0) {
+            atomicMin(&s_rng[0], mnU); atomicMax(&s_rng[1], mxU); atomicMin(&s_rng[2], mnV); atomicMax(&s_rng[3], mxV);
+        }
+    }
+    __syncthreads();
+    const int minOu = s_rng[0], minOv = s_rng[2];
+    const int RU = CT_U + (s_rng[1] - minOu), RV = CT_V + SPAN + (s_rng[3] - minOv);
+    const bool staged = RU <= RU_MAX && RV <= RV_MAX;  // CTA-uniform
+
+    // ---- B. stage the frame-1 region ------------------------------------------------------------------------------
+    const int cb = U0 + minOu;            // first column any candidate reads
+    const int ca = cb & ~3;               // 16-byte aligned start of the staged rows
+    const int sh = cb - ca;
+    const int rb = V0 + minOv + LO;       // first row any candidate reads
+    if (staged) {
+        const bool interior = ca >= 0 && ca + SP <= vw.pitch && cb + RU <= vw.dimU && rb >= 0 && rb + RV <= vw.dimV;
+        if (interior) {
+            const int c4 = tid & 15;
+            if (c4 < SP / 4) {
+                const uint32_t* __restrict__ src = vw.p1 + ca + c4 * 4;
+                for (int r = tid >> 4; r < RV; r += 16)
+                    *reinterpret_cast<uint4*>(&s_f1[r * SP + c4 * 4]) = __ldg(reinterpret_cast<const uint4*>(rowPtr(src, vw.pitch, rb + r)));
+            }
+        } else {
+            for (int idx = tid; idx < RV * SP; idx += 256) {
+                const int r = idx / SP, c = idx - r * SP;
+                s_f1[idx] = __ldg(rowPtr(vw.p1 + mirrorSearch(ca + c, vw.dimU), vw.pitch, mirrorSearch(rb + r, vw.dimV)));
+            }
+        }
+    }
+    __syncthreads();
+
+    // ---- C. SADs, reduction per window ----------------------------------------------------------------------------
+    const bool small = ws <= 4;
+    const int cu = U0 + lane;
+    const int gh = ws < 4 ? ws : 4;
+    const bool b0 = lane & 1, b1 = lane & 2, b2 = lane & 4, b3 = lane & 8;
+#pragma unroll 1
+    for (int strip = 0; strip < 2; ++strip) {
+        const int rowBase = V0 + warp * 8 + strip * 4;
+#pragma unroll 1
+        for (int g = 0; g < 4; g += gh) {
+            const int cv0 = rowBase + g;
+            const int wu = cu >> wsLog2, wv = cv0 >> wsLog2;
+            const int wx = View<STEP>::wx(wu, wv), wy = View<STEP>::wy(wu, wv);
+            const bool pixOk = cu < vw.lu && cv0 < vw.lv;
+            const bool winOk = (wu << wsLog2) < vw.lu && cv0 < vw.lv;
+            const int packed = s_off[(wv - (V0 >> wsLog2)) * nwu + (wu - (U0 >> wsLog2))];
+            const int ou = (int)(short)(packed & 0xffff), ov = packed >> 16;
+            const int ox = STEP == 1 ? ou : ov, oy = STEP == 1 ? ov : ou;
+            uint32_t acc[16];
+#pragma unroll
+            for (int z = 0; z < 16; ++z) acc[z] = 0;
+            if (pixOk) {
+                if (staged) {
+                    // word index of (row cv0 + ov + LO, column cu + ou) inside the staged region
+                    const uint32_t* __restrict__ q = &s_f1[(cv0 - V0 + ov - minOv) * SP + (lane + ou - minOu + sh)];
+#pragma unroll
+                    for (int r = 0; r < 4; ++r) {
+                        if (r < gh && cv0 + r < vw.lv) {
+                            const uint32_t f2 = __ldg(rowPtr(vw.p2 + cu, vw.pitch, cv0 + r));
+#pragma unroll
+                            for (int z = 0; z < R; ++z) acc[z] = sad4(q[(r + candOffset<R>(z) - LO) * SP], f2, acc[z]);
+                        }
+                    }
+                } else {
+                    const uint32_t* __restrict__ col = vw.p1 + mirrorSearch(cu + ou, vw.dimU);
+                    for (int r = 0; r < gh; ++r) {
+                        if (cv0 + r >= vw.lv) break;
+                        const uint32_t f2 = __ldg(rowPtr(vw.p2 + cu, vw.pitch, cv0 + r));
+                        const int bv = cv0 + r + ov;
+#pragma unroll
+                        for (int z = 0; z < R; ++z) acc[z] = sad4(__ldg(rowPtr(col, vw.pitch, mirrorSearch(bv + candOffset<R>(z), vw.dimV))), f2, acc[z]);
+                    }
+                }
+            }
+
+            if (small) {
+                bfly<16>(acc, 1, b0);
+                int n = 8, zbase = b0 ? 8 : 0;
+                if (ws == 4) {
+                    bfly<8>(acc, 2, b1);
+                    n = 4;
+                    zbase += b1 ? 4 : 0;
+                }
+                WindowCtx c;
+                c.o = 0;
+                if (winOk) c = loadWindowCtx<STEP>(a, wx, wy, ox, oy);
+                unsigned long long best = ~0ull;
+                if (winOk) {
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        const int z = zbase + i;
+                        if (i < n && z < R) {
+                            const uint32_t total = windowTotal<R>(a, c, acc[i], z);
+                            tapTotal<R>(a, wx, wy, z, total);
+                            best = min(best, layerKey(total, z));
+                        }
+                    }
+                }
+                best = min(best, shflXor64(best, 1));
+                if (ws == 4) best = min(best, shflXor64(best, 2));
+                if (winOk && (lane & (ws - 1)) == 0) commitWindow<R, STEP>(a, wx, wy, c.o, (int)(best & 0xff));
+            } else {
+                bfly<16>(acc, 1, b0);
+                bfly<8>(acc, 2, b1);
+                bfly<4>(acc, 4, b2);
+                int z0 = (b0 ? 8 : 0) + (b1 ? 4 : 0) + (b2 ? 2 : 0);
+                const int lwin = ((cv0 - V0) >> wsLog2) * nwu + (lane >> wsLog2);
+                if (ws == 8) {
+                    atomicAdd(&s_sums[lwin][z0], acc[0]);
+                    atomicAdd(&s_sums[lwin][z0 + 1], acc[1]);
+                } else {  // ws == 16
+                    bfly<2>(acc, 8, b3);
+                    z0 += b3 ? 1 : 0;
+                    atomicAdd(&s_sums[lwin][z0], acc[0]);
+                }
+            }
+        }
+    }
+
+    if (!small) {
+        __syncthreads();
+        if (tid < nwu * nwv) {
+            const int wu = (U0 >> wsLog2) + (tid % nwu), wv = (V0 >> wsLog2) + (tid / nwu);
+            const int wx = View<STEP>::wx(wu, wv), wy = View<STEP>::wy(wu, wv);
+            if (wx < a.nWx && wy < a.nWy) finalizeWindow<R, STEP>(a, wx, wy, s_sums[tid]);
+        }
+    }
+}
+
+template <int R> int launchCandR(hrb_ofc* h, const SearchArgs& a, int step) {
+    const dim3 block(32, 8, 1);
+    const int lu = step == 1 ? a.lw : a.lh, lv = step == 1 ? a.lh : a.lw;
+    const dim3 grid((lu + CT_U - 1) / CT_U, (lv + CT_V - 1) / CT_V, 1);
+    if (step == 1)
+        sadCandKernel<R, 1><<<grid, block, 0, h->stream>>>(a);
+    else
+        sadCandKernel<R, 0><<<grid, block, 0, h->stream>>>(a);
+    HRB_LAUNCH_CHECK();
+    return HRB_OK;
+}
+
+}  // namespace
+
+// One whole pass (SAD + arg-min + offset update) for 2 <= ws <= 16 at full flow resolution.
+int launchSearchPassCand(hrb_ofc* h, const SearchArgs& a, int R, int step) {
+    switch (R) {
+#define HRB_CASE(N) case N: return launchCandR<N>(h, a, step);
+        HRB_CASE(5) HRB_CASE(6) HRB_CASE(7) HRB_CASE(8) HRB_CASE(9) HRB_CASE(10) HRB_CASE(11) HRB_CASE(12) HRB_CASE(13) HRB_CASE(14)
+        HRB_CASE(15) HRB_CASE(16)
+#undef HRB_CASE
+        default: return -1;
+    }
+}
+
+}  // namespace hrb

@@ -115,8 +115,20 @@ class OpticalFlowCalc:
     def calculateOpticalFlowAsync(self):
         self._check(self._lib.hrb_ofc_calculate_optical_flow_async(self._h))
 
+    def updateFrameAsync(self, pinnedInputPlanes):
+        self._check(self._lib.hrb_ofc_update_frame_async(self._h, _ptr(pinnedInputPlanes)))
+
+    def waitUpload(self):
+        self._check(self._lib.hrb_ofc_wait_upload(self._h))
+
     def downloadFrameAsync(self, pinnedOutputPlanes):
-        self._check(self._lib.hrb_ofc_download_frame_async(self._h, _ptr(pinnedOutputPlanes)))
+        """Enqueue the download; returns the ticket for waitDownload()."""
+        t = C.c_ulonglong()
+        self._check(self._lib.hrb_ofc_download_frame_async(self._h, _ptr(pinnedOutputPlanes), C.byref(t)))
+        return t.value
+
+    def waitDownload(self, ticket):
+        self._check(self._lib.hrb_ofc_wait_download(self._h, ticket))
 
     def synchronize(self):
         self._check(self._lib.hrb_ofc_synchronize(self._h))

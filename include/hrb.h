@@ -128,10 +128,19 @@ HRB_API int hrb_ofc_reset(hrb_ofc* h); /* == hrb_ofc_set_frame_count(h, 0) */
 /* ---- device-resident variants (benchmark / zero-copy callers) ---------------------------------- */
 /* Same as hrb_ofc_update_frame but the source is already in device memory of the handle's GPU. */
 HRB_API int hrb_ofc_update_frame_device(hrb_ofc* h, const void* device_planes);
-/* Device address of the output frame (valid until destroy; written by warp_frames / copy_frame). */
+/* Device address of the output frame most recently written by warp_frames / copy_frame (one of a ring of three:
+ * the slot advances with every download; without downloads it never changes). */
 HRB_API int hrb_ofc_output_device_ptr(hrb_ofc* h, void** out);
-/* Asynchronous variant of download_frame into PINNED host memory; completes at hrb_ofc_synchronize. */
-HRB_API int hrb_ofc_download_frame_async(hrb_ofc* h, uint8_t* pinned_output_planes);
+/* Asynchronous variants for PINNED host memory.  Transfers run on their own streams: the upload of the next source
+ * frame and the downloads of the current outputs overlap the kernels (the output frame is a ring of three on the
+ * device, the upload has its own input slot).
+ *   update_frame_async : the buffer must stay untouched until hrb_ofc_wait_upload (or synchronize) returns.
+ *   download_frame_async: hands out a ticket; the buffer is valid after hrb_ofc_wait_download(ticket) (tickets may be
+ *                         waited for in any order; only the 16 most recent ones are tracked, older ones have completed). */
+HRB_API int hrb_ofc_update_frame_async(hrb_ofc* h, const uint8_t* pinned_input_planes);
+HRB_API int hrb_ofc_wait_upload(hrb_ofc* h);
+HRB_API int hrb_ofc_download_frame_async(hrb_ofc* h, uint8_t* pinned_output_planes, unsigned long long* ticket);
+HRB_API int hrb_ofc_wait_download(hrb_ofc* h, unsigned long long ticket);
 /* calculate_optical_flow without the final host wait (statistics are resolved at the next synchronize). */
 HRB_API int hrb_ofc_calculate_optical_flow_async(hrb_ofc* h);
 HRB_API int hrb_ofc_synchronize(hrb_ofc* h);

@@ -356,3 +356,50 @@ def test_levels_exhaustive(black, white):
         g.downloadFrame(a)
         o.downloadFrame(b)
         assert np.array_equal(a, b), f"warpFrames hdr={hdr}: {np.count_nonzero(a != b)} differ"
+
+
+@pytest.mark.parametrize("hdr", [False, True])
+def test_pipelined_transfers_match_the_oracle(synth, hdr):
+    """Asynchronous upload / download entry points (own streams, 4 input slots, ring of 3 output frames, tickets):
+    every delivered frame equals the oracle's, whatever the overlap."""
+    import torch
+    W, H = 320, 176
+    g, o = make_pair(hdr, H, W, R=9)
+    dt = torch.int16 if hdr else torch.uint8
+    n_el = g.outputFrameBytes // (2 if hdr else 1)
+    pool = [torch.zeros(n_el, dtype=dt).pin_memory() for _ in range(12)]
+    fs = frames(synth, W, H, hdr, 7)
+    pins = [torch.from_numpy(f.view(np.int16) if hdr else f).pin_memory() for f in fs]
+    expected, tickets = [], []
+    k = 0
+    for t, fr in enumerate(fs):
+        g.updateFrameAsync(pins[t])
+        o.updateFrame(fr)
+        if t >= 2:
+            g.calculateOpticalFlowAsync()
+            o.calculateOpticalFlow()
+        for j in range(3):
+            blend = (0.4 * (3 * t + j)) % 1.0
+            if t >= 2:
+                g.warpFrames(blend, 2)
+                o.warpFrames(blend, 2)
+            else:
+                g.copyFrame()
+                o.copyFrame()
+            tickets.append((g.downloadFrameAsync(pool[k % len(pool)]), k % len(pool)))
+            b = out_array(o, hdr)
+            o.downloadFrame(b)
+            expected.append(b)
+            k += 1
+            if len(tickets) > 9:   # consume in order, a few frames behind
+                tk, slot = tickets.pop(0)
+                g.waitDownload(tk)
+                got = pool[slot].numpy().view(np.uint16 if hdr else np.uint8)
+                assert np.array_equal(got, expected.pop(0)), f"delivered frame {k - len(tickets) - 1} differs"
+    while tickets:
+        tk, slot = tickets.pop(0)
+        g.waitDownload(tk)
+        got = pool[slot].numpy().view(np.uint16 if hdr else np.uint8)
+        assert np.array_equal(got, expected.pop(0))
+    g.synchronize()
+    assert g.m_frameCount == 7 and g.m_totalFrameDelta == o.state().totalFrameDelta
