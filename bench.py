@@ -36,6 +36,8 @@ WORKLOADS = {
     "cfg3": dict(W=3840, H=2160, hdr=True, maxres=2160, target=69444, desc="3840x2160 P010 HDR 23.976->144 fps, full-resolution flow"),
     "cfg2": dict(W=1920, H=1080, hdr=False, maxres=540, target=69444, desc="1920x1080 NV12 SDR 23.976->144 fps, half-resolution flow"),
     "cfg1": dict(W=1920, H=1080, hdr=False, maxres=270, target=166667, desc="1920x1080 NV12 SDR 24->60 fps, 270p flow"),
+    "cfg4": dict(W=7680, H=4320, hdr=True, maxres=4320, target=69444, desc="7680x4320 P010 HDR 23.976->144 fps, full-resolution flow, ONE stream "
+                 "split spatially over the GPUs (NVLink all-gather of the ingested stripes, per-GPU warp + egress of its stripe)"),
 }
 SEARCH_RADIUS = 16
 METRIC = "interpolated frames/s at 4K P010 (flow + warp, R=16)"
@@ -222,6 +224,84 @@ def cpu_baseline(wl):
 
 
 # ------------------------------------------------------------------------------------------------------
+# configs[3]: one 8K stream split spatially over the GPUs (strong scaling)
+# ------------------------------------------------------------------------------------------------------
+def run_split(args, wl):
+    import torch
+    import torch.distributed as dist
+
+    import hopperrender_b200 as hr
+    from hopperrender_b200 import replay, shard, synth
+    from hopperrender_b200.split import SpatialSplitStream
+
+    rank, world, local = dist_env()
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    W, H, hdr = wl["W"], wl["H"], wl["hdr"]
+    cls = hr.OpticalFlowCalcHDR if hdr else hr.OpticalFlowCalcSDR
+    s = SpatialSplitStream(cls, H, W, 8, 6, 0.0, 255.0, wl["maxres"], rank=rank, world_size=world)
+    s.calc.m_opticalFlowSearchRadius = args.radius
+    RING = 3
+    host = [torch.from_numpy(synth.make_frame(W, H, t, synth.SEED_BASE + 4, hdr, noise=False).view(np.int16 if hdr else np.uint8)).pin_memory()
+            for t in range(RING)]
+    POOL = 10
+    pool = [torch.empty_like(host[0]).pin_memory() for _ in range(POOL)]
+    sched = replay.output_schedule(3 * (args.steps + args.warmup) + 16, wl["target"], replay.SOURCE_FRAME_TIME_23976)
+    pending, k = [], [0]
+
+    def step(i):
+        s.update_frame(host[i % RING])
+        s.calculate_optical_flow()
+        for b in sched[i]:
+            pending.append(s.warp_and_download(b, hr.BlendedFrame, pool[k[0] % POOL]))
+            k[0] += 1
+        while len(pending) > 7:
+            s.wait(pending.pop(0))
+        return len(sched[i])
+
+    idx = 0
+    for _ in range(max(args.warmup, 3)):
+        step(idx)
+        idx += 1
+    while pending:
+        s.wait(pending.pop(0))
+    s.calc.synchronize()
+    shard.barrier()
+    torch.cuda.synchronize()
+    launches0 = hr.kernel_launch_count()
+    t0 = time.perf_counter()
+    frames = 0
+    for _ in range(args.steps):
+        frames += step(idx)
+        idx += 1
+    while pending:
+        s.wait(pending.pop(0))
+    s.calc.synchronize()
+    shard.barrier()
+    torch.cuda.synchronize()
+    ms = shard.combine(0, (time.perf_counter() - t0) * 1e3)[1]
+    launches = shard.combine(hr.kernel_launch_count() - launches0, 0)[0]
+    if rank == 0:
+        value = frames / (ms * 1e-3)  # every rank delivers a stripe of the SAME frames: the stream's rate, not a sum
+        line = {
+            "metric": "interpolated frames/s of one 8K P010 stream (flow + warp, R=16), spatially split", "value": value, "unit": UNIT,
+            "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+            "config": {"workload": f"cfg4: {wl['desc']}, R={args.radius}", "stripe_rows": H // world,
+                       "collective": "NCCL all-gather of the ingested frame stripes (2 per source frame); search replicated; no other exchange",
+                       "realtime_factor_vs_144fps": value / 144.0},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": int(s.stripe_bytes()),
+                    "d2h_bytes_per_step": int(round(frames / args.steps * s.stripe_bytes())), "note": "bytes per rank"},
+            "gpu_launches": int(launches),
+        }
+        print(json.dumps(line), flush=True)
+    s.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+# ------------------------------------------------------------------------------------------------------
 # the CUDA arm
 # ------------------------------------------------------------------------------------------------------
 def main():
@@ -238,6 +318,9 @@ def main():
     wl = WORKLOADS[args.workload]
     if args.impl == "reference":
         run_reference(args, wl, args.workload)
+        return
+    if args.workload == "cfg4":
+        run_split(args, wl)
         return
 
     import torch

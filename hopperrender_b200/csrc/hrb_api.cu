@@ -317,7 +317,16 @@ static int enqueueDownload(hrb_ofc* h, uint8_t* dst, unsigned long long* ticket)
     HRB_CUDA(cudaSetDevice(h->device));
     const int slot = h->outCur;
     HRB_CUDA(cudaStreamWaitEvent(h->downStream, h->outReady[slot], 0));
-    HRB_CUDA(cudaMemcpyAsync(dst, h->outputRing[slot], h->outFrameBytes, cudaMemcpyDeviceToHost, h->downStream));
+    if (h->stripeY0 == 0 && h->stripeY1 == h->frameHeight) {
+        HRB_CUDA(cudaMemcpyAsync(dst, h->outputRing[slot], h->outFrameBytes, cudaMemcpyDeviceToHost, h->downStream));
+    } else {
+        // only the stripe's luma rows and their chroma rows travel, to the same offsets of the caller's full-frame buffer
+        const size_t rowBytes = (size_t)h->outputStride * h->bpp;
+        const size_t lumaOff = (size_t)h->stripeY0 * rowBytes, lumaLen = (size_t)(h->stripeY1 - h->stripeY0) * rowBytes;
+        const size_t chromaOff = ((size_t)h->frameHeight + (h->stripeY0 >> 1)) * rowBytes, chromaLen = lumaLen / 2;
+        HRB_CUDA(cudaMemcpyAsync(dst + lumaOff, h->outputRing[slot] + lumaOff, lumaLen, cudaMemcpyDeviceToHost, h->downStream));
+        HRB_CUDA(cudaMemcpyAsync(dst + chromaOff, h->outputRing[slot] + chromaOff, chromaLen, cudaMemcpyDeviceToHost, h->downStream));
+    }
     HRB_CUDA(cudaEventRecord(h->outFree[slot], h->downStream));
     const unsigned long long seq = ++h->downloadSeq;
     HRB_CUDA(cudaEventRecord(h->ticketEvent[seq % hrb_ofc::kTickets], h->downStream));
@@ -423,6 +432,8 @@ int hrb_ofc_create(hrb_ofc** out, const hrb_ofc_desc* d) {
     h->spareFreeEvent = nullptr;
     h->outCur = h->outView = 0;
     h->downloadSeq = 0;
+    h->stripeY0 = 0;
+    h->stripeY1 = d->frame_height;
     h->levelOffsets[0][0] = h->levelOffsets[0][1] = h->levelOffsets[1][0] = h->levelOffsets[1][1] = nullptr;
     h->winSums = nullptr;
     h->offsetArrayScratch = nullptr;
@@ -897,6 +908,15 @@ int hrb_ofc_profile_reset(hrb_ofc* h) {
         h->prof.ms[i] = 0;
         h->prof.n[i] = 0;
     }
+    return HRB_OK;
+}
+
+int hrb_ofc_set_output_stripe(hrb_ofc* h, int row_begin, int row_end) {
+    HRB_REQUIRE(h, "null handle");
+    HRB_REQUIRE(row_begin >= 0 && row_end <= h->frameHeight && row_begin < row_end, "stripe outside the frame");
+    HRB_REQUIRE((row_begin % 2) == 0 && (row_end % 2) == 0, "stripe bounds must be even (chroma rows are shared by luma row pairs)");
+    h->stripeY0 = row_begin;
+    h->stripeY1 = row_end;
     return HRB_OK;
 }
 

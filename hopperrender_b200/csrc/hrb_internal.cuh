@@ -146,6 +146,7 @@ struct hrb_ofc {
     int planePitch;                // words
     uint32_t* searchPlaneT[4];     // transposed copy of searchPlane (X steps read these so that their accesses are row segments too)
     int planePitchT;               // words
+    int stripeY0, stripeY1;        // output stripe (luma rows) warpFrames / copyFrame / downloadFrame work on; default the whole frame
     uint8_t* outputRing[3];        // m_outputFrameArray, as a ring so that a download can overlap the next warp
     int16_t* levelOffsets[2][2];   // [iteration parity][axis] window-level offsets
     size_t levelCapacity;          // entries per level array

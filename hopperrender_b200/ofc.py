@@ -133,6 +133,9 @@ class OpticalFlowCalc:
     def synchronize(self):
         self._check(self._lib.hrb_ofc_synchronize(self._h))
 
+    def setOutputStripe(self, rowBegin, rowEnd):
+        self._check(self._lib.hrb_ofc_set_output_stripe(self._h, int(rowBegin), int(rowEnd)))
+
     def outputDevicePtr(self):
         p = C.c_void_p()
         self._check(self._lib.hrb_ofc_output_device_ptr(self._h, C.byref(p)))

@@ -152,6 +152,13 @@ HRB_API int hrb_host_unregister(void* ptr);
 HRB_API int hrb_host_alloc(void** out, size_t bytes);
 HRB_API int hrb_host_free(void* ptr);
 
+/* ---- spatial split of one stream over several GPUs ----------------------------------------------------------- */
+/* Restrict warp_frames / copy_frame / download_frame to the luma rows [row_begin, row_end) (even bounds) and the
+ * chroma rows that belong to them.  Every GPU of the split holds the full source frames and the full flow (the
+ * search is replicated, it is not the PCIe-bound part); each produces and downloads only its stripe, into the same
+ * offsets of a full-frame host buffer.  Default: the whole frame. */
+HRB_API int hrb_ofc_set_output_stripe(hrb_ofc* h, int row_begin, int row_end);
+
 /* ---- test taps --------------------------------------------------------------------------------- */
 /* With tap mode on, calculate_optical_flow also records, per (iteration, step) pass: the window sums,
  * the winning layer per window and the offset field after the update.  Off by default (costs memory). */

@@ -403,3 +403,37 @@ def test_pipelined_transfers_match_the_oracle(synth, hdr):
         assert np.array_equal(got, expected.pop(0))
     g.synchronize()
     assert g.m_frameCount == 7 and g.m_totalFrameDelta == o.state().totalFrameDelta
+
+
+@pytest.mark.parametrize("hdr,mode", [(False, 2), (True, 2), (True, 3), (False, 6)])
+def test_output_stripes_tile_the_full_frame(synth, hdr, mode):
+    """hrb_ofc_set_output_stripe: four calculators fed the same frames, each producing one quarter of the rows (what the
+    ranks of a spatial split do), together reproduce the single-calculator output — warp, copy and download."""
+    from hopperrender_b200.split import merge_stripes, stripe_bounds
+    W, H, n = 256, 160, 4
+    full, o = make_pair(hdr, H, W, R=8)
+    parts = [make_pair(hdr, H, W, R=8)[0] for _ in range(n)]
+    for p, (y0, y1) in zip(parts, stripe_bounds(H, n)):
+        p.setOutputStripe(y0, y1)
+    for t, fr in enumerate(frames(synth, W, H, hdr, 4)):
+        for c in [full, o] + parts:
+            c.updateFrame(fr)
+        if t >= 2:
+            for c in [full, o] + parts:
+                c.calculateOpticalFlow()
+    for op in ("warp", "copy"):
+        outs = []
+        for c in [full, o] + parts:
+            if op == "warp":
+                c.warpFrames(0.3, mode)
+            else:
+                c.copyFrame()
+            a = out_array(full, hdr)
+            c.downloadFrame(a)
+            outs.append(a)
+        merged = merge_stripes(outs[2:], H, W)
+        if mode != 3:
+            assert np.array_equal(outs[0], outs[1])
+        assert np.array_equal(merged, outs[0]), f"{op}: stripes do not tile the full frame"
+        # a stripe download must leave the rest of the caller's buffer alone
+        assert not outs[2][W * (H // n):W * H].any()

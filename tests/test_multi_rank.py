@@ -69,3 +69,14 @@ def test_reference_arm_line_has_the_contract_keys():
         assert k in line
     assert line["impl"] == "reference" and line["value"] > 0 and line["cpu_baseline"]["kind"] in ("port", "reference")
     assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["e2e"]["d2h_bytes_per_step"] == 0
+
+
+def test_stripe_bounds_are_even_and_tile_the_frame():
+    from hopperrender_b200.split import stripe_bounds
+    for H, w in [(4320, 8), (4320, 4), (4320, 2), (2160, 8), (288, 2), (64, 1)]:
+        b = stripe_bounds(H, w)
+        assert b[0][0] == 0 and b[-1][1] == H
+        assert all(y0 % 2 == 0 and y1 % 2 == 0 and y1 > y0 for y0, y1 in b)
+        assert all(b[i][1] == b[i + 1][0] for i in range(w - 1))
+    with pytest.raises(ValueError):
+        stripe_bounds(1080, 16)
