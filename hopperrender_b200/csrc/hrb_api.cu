@@ -922,9 +922,9 @@ int hrb_ofc_set_output_stripe(hrb_ofc* h, int row_begin, int row_end) {
 
 int hrb_ofc_set_search_variant(hrb_ofc* h, int variant) {
     HRB_REQUIRE(h, "null handle");
-    HRB_REQUIRE(variant == 0 || variant == 1, "variant must be 0 (automatic) or 1 (generic kernels only)");
+    HRB_REQUIRE(variant >= 0 && variant <= 2, "variant must be 0 (automatic), 1 (generic kernels only) or 2 (L1-fed sliding kernel)");
     h->searchVariant = variant;
-    h->warpVariant = variant;
+    h->warpVariant = variant == 1 ? 1 : 0;
     return HRB_OK;
 }
 

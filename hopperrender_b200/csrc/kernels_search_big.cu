@@ -106,19 +106,90 @@ template <int R, int STEP, int NWARPS> __global__ void __launch_bounds__(32 * NW
     reduceAndEmit<R, STEP>(a, acc, lane, wx, wy, ox, oy);
 }
 
-template <int R> int launchBigR(hrb_ofc* h, const SearchArgs& a, int step) {
-    constexpr int NWARPS = 4;
-    const dim3 block(32, NWARPS, 1);
-    if (step == 1) {
-        const dim3 grid((a.lw + 31) / 32, (a.lh + 32 * NWARPS - 1) / (32 * NWARPS), 1);
-        sadSlideKernel<R, 1, NWARPS><<<grid, block, 0, h->stream>>>(a);
+// ---- the sliding kernel with the frame-1 rows staged in shared memory -------------------------------------------
+// CTA = NW warps stacked along v inside ONE window (32 x 32*NW pixels, NW = min(ws, 128) / 32).  The 32*NW + (HI-LO)
+// frame-1 rows the tile can touch are copied once with 16-byte loads (through the mirror at the frame border); the
+// sliding loop then reads them with LDS at compile-time offsets: no per-fetch address arithmetic is left on the ALU
+// pipe, and rows shared by the stacked runs cross L2 -> SM once.
+constexpr int SSP = 36;  // staged row pitch in words: 32 + alignment slack, 9 x 16 B
+
+template <int R, int STEP, int NW> __global__ void __launch_bounds__(32 * NW) sadSlideStagedKernel(const SearchArgs a) {
+    constexpr int LO = CandSpan<R>::LO, SPAN = CandSpan<R>::SPAN;
+    constexpr int ROWS = 32 * NW + SPAN;
+    __shared__ __align__(16) uint32_t s_f1[ROWS * SSP];
+    const View<STEP> vw(a);
+    const int lane = threadIdx.x, warp = threadIdx.y;
+    const int tid = warp * 32 + lane;
+    const int U0 = blockIdx.x * 32, V0 = blockIdx.y * 32 * NW;
+    const int wu = U0 >> a.wsLog2, wv = V0 >> a.wsLog2;
+    const int wx = View<STEP>::wx(wu, wv), wy = View<STEP>::wy(wu, wv);
+    int ox, oy;
+    loadWindowOffsets<STEP>(a, wx, wy, ox, oy);
+    const int ou = View<STEP>::ou(ox, oy), ov = View<STEP>::ov(ox, oy);
+
+    // frame-2 run of this thread first: its 32 loads are in flight while the CTA stages frame 1
+    const int cu = U0 + lane, v0 = V0 + warp * 32;
+    const bool runOk = v0 < vw.lv && cu < vw.lu;
+    const int np = min(32, vw.lv - v0);
+    uint32_t f2[32];
+    if (runOk) {
+        const uint32_t* __restrict__ p2 = rowPtr(vw.p2 + cu, vw.pitch, v0);
+#pragma unroll
+        for (int p = 0; p < 32; ++p) f2[p] = __ldg(rowPtr(p2, vw.pitch, np == 32 ? p : min(p, np - 1)));
+    }
+
+    // stage rows V0+ov+LO .. +ROWS-1, columns U0+ou .. +31 (16-byte aligned superset)
+    const int cb = U0 + ou, ca = cb & ~3, sh = cb - ca;
+    const int rb = V0 + ov + LO;
+    const int rowsNeeded = min(ROWS, (vw.lv - V0) + SPAN);  // tiles cut by the flow's last row need fewer rows
+    if (ca >= 0 && ca + SSP <= vw.pitch && cb + 32 <= vw.dimU && rb >= 0 && rb + rowsNeeded <= vw.dimV) {
+        constexpr int RPI = (32 * NW) / 9;  // rows copied per iteration: 9 threads x 16 B per row
+        if (tid < RPI * 9) {
+            const int c4 = tid % 9;
+            const uint32_t* __restrict__ src = vw.p1 + ca + c4 * 4;
+            for (int r = tid / 9; r < rowsNeeded; r += RPI) cpAsync16(&s_f1[r * SSP + c4 * 4], rowPtr(src, vw.pitch, rb + r));
+        }
+        cpAsyncWaitAll();
     } else {
-        const dim3 grid((a.lh + 31) / 32, (a.lw + 32 * NWARPS - 1) / (32 * NWARPS), 1);
-        sadSlideKernel<R, 0, NWARPS><<<grid, block, 0, h->stream>>>(a);
+        for (int idx = tid; idx < rowsNeeded * SSP; idx += 32 * NW) {
+            const int r = idx / SSP, c = idx - r * SSP;
+            s_f1[idx] = __ldg(rowPtr(vw.p1 + mirrorSearch(ca + c, vw.dimU), vw.pitch, mirrorSearch(rb + r, vw.dimV)));
+        }
+    }
+    __syncthreads();
+
+    uint32_t acc[16];
+#pragma unroll
+    for (int z = 0; z < 16; ++z) acc[z] = 0;
+    if (v0 < vw.lv) {  // warp-uniform
+        if (runOk) {
+            const uint32_t* __restrict__ q = &s_f1[(warp * 32) * SSP + lane + sh];
+            if (np == 32)
+                slidingSad<R, false>(acc, f2, 32, [&](int j) { return q[j * SSP]; });
+            else
+                slidingSad<R, true>(acc, f2, np, [&](int j) { return q[j * SSP]; });  // rows past the staged ones are never consumed
+        }
+        reduceAndEmit<R, STEP>(a, acc, lane, wx, wy, ox, oy);
+    }
+}
+
+template <int R, int STEP> int launchBigStep(hrb_ofc* h, const SearchArgs& a) {
+    const int lu = STEP == 1 ? a.lw : a.lh, lv = STEP == 1 ? a.lh : a.lw;
+    if (h->searchVariant == 2) {  // the L1-fed variant (A/B)
+        constexpr int NWARPS = 4;
+        sadSlideKernel<R, STEP, NWARPS><<<dim3((lu + 31) / 32, (lv + 32 * NWARPS - 1) / (32 * NWARPS), 1), dim3(32, NWARPS, 1), 0, h->stream>>>(a);
+    } else if (a.ws >= 128) {
+        sadSlideStagedKernel<R, STEP, 4><<<dim3((lu + 31) / 32, (lv + 127) / 128, 1), dim3(32, 4, 1), 0, h->stream>>>(a);
+    } else if (a.ws == 64) {
+        sadSlideStagedKernel<R, STEP, 2><<<dim3((lu + 31) / 32, (lv + 63) / 64, 1), dim3(32, 2, 1), 0, h->stream>>>(a);
+    } else {
+        sadSlideStagedKernel<R, STEP, 1><<<dim3((lu + 31) / 32, (lv + 31) / 32, 1), dim3(32, 1, 1), 0, h->stream>>>(a);
     }
     HRB_LAUNCH_CHECK();
     return HRB_OK;
 }
+
+template <int R> int launchBigR(hrb_ofc* h, const SearchArgs& a, int step) { return step == 1 ? launchBigStep<R, 1>(h, a) : launchBigStep<R, 0>(h, a); }
 
 }  // namespace
 

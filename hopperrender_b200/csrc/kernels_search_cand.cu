@@ -78,9 +78,9 @@ template <int R, int STEP> __global__ void __launch_bounds__(256) sadCandKernel(
             const int c4 = tid & 15;
             if (c4 < SP / 4) {
                 const uint32_t* __restrict__ src = vw.p1 + ca + c4 * 4;
-                for (int r = tid >> 4; r < RV; r += 16)
-                    *reinterpret_cast<uint4*>(&s_f1[r * SP + c4 * 4]) = __ldg(reinterpret_cast<const uint4*>(rowPtr(src, vw.pitch, rb + r)));
+                for (int r = tid >> 4; r < RV; r += 16) cpAsync16(&s_f1[r * SP + c4 * 4], rowPtr(src, vw.pitch, rb + r));
             }
+            cpAsyncWaitAll();
         } else {
             for (int idx = tid; idx < RV * SP; idx += 256) {
                 const int r = idx / SP, c = idx - r * SP;
@@ -91,90 +91,91 @@ template <int R, int STEP> __global__ void __launch_bounds__(256) sadCandKernel(
     __syncthreads();
 
     // ---- C. SADs, reduction per window ----------------------------------------------------------------------------
+    // a warp owns 8 consecutive v; they are accumulated in groups of min(ws, 8) rows (one window row each) before the
+    // lanes are reduced, so the reduction is paid once per 8 rows for ws >= 8
     const bool small = ws <= 4;
     const int cu = U0 + lane;
-    const int gh = ws < 4 ? ws : 4;
+    const int gh = ws < 8 ? ws : 8;
     const bool b0 = lane & 1, b1 = lane & 2, b2 = lane & 4, b3 = lane & 8;
 #pragma unroll 1
-    for (int strip = 0; strip < 2; ++strip) {
-        const int rowBase = V0 + warp * 8 + strip * 4;
-#pragma unroll 1
-        for (int g = 0; g < 4; g += gh) {
-            const int cv0 = rowBase + g;
-            const int wu = cu >> wsLog2, wv = cv0 >> wsLog2;
-            const int wx = View<STEP>::wx(wu, wv), wy = View<STEP>::wy(wu, wv);
-            const bool pixOk = cu < vw.lu && cv0 < vw.lv;
-            const bool winOk = (wu << wsLog2) < vw.lu && cv0 < vw.lv;
-            const int packed = s_off[(wv - (V0 >> wsLog2)) * nwu + (wu - (U0 >> wsLog2))];
-            const int ou = (int)(short)(packed & 0xffff), ov = packed >> 16;
-            const int ox = STEP == 1 ? ou : ov, oy = STEP == 1 ? ov : ou;
-            uint32_t acc[16];
+    for (int g = 0; g < 8; g += gh) {
+        const int cv0 = V0 + warp * 8 + g;
+        const int wu = cu >> wsLog2, wv = cv0 >> wsLog2;
+        const int wx = View<STEP>::wx(wu, wv), wy = View<STEP>::wy(wu, wv);
+        const bool pixOk = cu < vw.lu && cv0 < vw.lv;
+        const bool winOk = (wu << wsLog2) < vw.lu && cv0 < vw.lv;
+        const int packed = s_off[(wv - (V0 >> wsLog2)) * nwu + (wu - (U0 >> wsLog2))];
+        const int ou = (int)(short)(packed & 0xffff), ov = packed >> 16;
+        const int ox = STEP == 1 ? ou : ov, oy = STEP == 1 ? ov : ou;
+        uint32_t acc[16];
 #pragma unroll
-            for (int z = 0; z < 16; ++z) acc[z] = 0;
-            if (pixOk) {
-                if (staged) {
-                    // word index of (row cv0 + ov + LO, column cu + ou) inside the staged region
-                    const uint32_t* __restrict__ q = &s_f1[(cv0 - V0 + ov - minOv) * SP + (lane + ou - minOu + sh)];
+        for (int z = 0; z < 16; ++z) acc[z] = 0;
+        if (pixOk) {
+            if (staged) {
+                // word index of (row cv0 + ov + LO, column cu + ou) inside the staged region
+                const uint32_t* __restrict__ q = &s_f1[(cv0 - V0 + ov - minOv) * SP + (lane + ou - minOu + sh)];
+                const uint32_t* __restrict__ p2 = rowPtr(vw.p2 + cu, vw.pitch, cv0);
+                uint32_t f2r[8];  // all frame-2 loads of the group are issued before the first one is consumed
 #pragma unroll
-                    for (int r = 0; r < 4; ++r) {
-                        if (r < gh && cv0 + r < vw.lv) {
-                            const uint32_t f2 = __ldg(rowPtr(vw.p2 + cu, vw.pitch, cv0 + r));
+                for (int r = 0; r < 8; ++r) f2r[r] = (r < gh && cv0 + r < vw.lv) ? __ldg(rowPtr(p2, vw.pitch, r)) : 0u;
 #pragma unroll
-                            for (int z = 0; z < R; ++z) acc[z] = sad4(q[(r + candOffset<R>(z) - LO) * SP], f2, acc[z]);
-                        }
+                for (int r = 0; r < 8; ++r) {
+                    if (r < gh && cv0 + r < vw.lv) {
+#pragma unroll
+                        for (int z = 0; z < R; ++z) acc[z] = sad4(q[(r + candOffset<R>(z) - LO) * SP], f2r[r], acc[z]);
                     }
-                } else {
-                    const uint32_t* __restrict__ col = vw.p1 + mirrorSearch(cu + ou, vw.dimU);
-                    for (int r = 0; r < gh; ++r) {
-                        if (cv0 + r >= vw.lv) break;
-                        const uint32_t f2 = __ldg(rowPtr(vw.p2 + cu, vw.pitch, cv0 + r));
-                        const int bv = cv0 + r + ov;
+                }
+            } else {
+                const uint32_t* __restrict__ col = vw.p1 + mirrorSearch(cu + ou, vw.dimU);
+                for (int r = 0; r < gh; ++r) {
+                    if (cv0 + r >= vw.lv) break;
+                    const uint32_t f2 = __ldg(rowPtr(vw.p2 + cu, vw.pitch, cv0 + r));
+                    const int bv = cv0 + r + ov;
 #pragma unroll
-                        for (int z = 0; z < R; ++z) acc[z] = sad4(__ldg(rowPtr(col, vw.pitch, mirrorSearch(bv + candOffset<R>(z), vw.dimV))), f2, acc[z]);
+                    for (int z = 0; z < R; ++z) acc[z] = sad4(__ldg(rowPtr(col, vw.pitch, mirrorSearch(bv + candOffset<R>(z), vw.dimV))), f2, acc[z]);
+                }
+            }
+        }
+
+        if (small) {
+            bfly<16>(acc, 1, b0);
+            int n = 8, zbase = b0 ? 8 : 0;
+            if (ws == 4) {
+                bfly<8>(acc, 2, b1);
+                n = 4;
+                zbase += b1 ? 4 : 0;
+            }
+            WindowCtx c;
+            c.o = 0;
+            if (winOk) c = loadWindowCtx<STEP>(a, wx, wy, ox, oy);
+            unsigned long long best = ~0ull;
+            if (winOk) {
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    const int z = zbase + i;
+                    if (i < n && z < R) {
+                        const uint32_t total = windowTotal<R>(a, c, acc[i], z);
+                        tapTotal<R>(a, wx, wy, z, total);
+                        best = min(best, layerKey(total, z));
                     }
                 }
             }
-
-            if (small) {
-                bfly<16>(acc, 1, b0);
-                int n = 8, zbase = b0 ? 8 : 0;
-                if (ws == 4) {
-                    bfly<8>(acc, 2, b1);
-                    n = 4;
-                    zbase += b1 ? 4 : 0;
-                }
-                WindowCtx c;
-                c.o = 0;
-                if (winOk) c = loadWindowCtx<STEP>(a, wx, wy, ox, oy);
-                unsigned long long best = ~0ull;
-                if (winOk) {
-#pragma unroll
-                    for (int i = 0; i < 8; ++i) {
-                        const int z = zbase + i;
-                        if (i < n && z < R) {
-                            const uint32_t total = windowTotal<R>(a, c, acc[i], z);
-                            tapTotal<R>(a, wx, wy, z, total);
-                            best = min(best, layerKey(total, z));
-                        }
-                    }
-                }
-                best = min(best, shflXor64(best, 1));
-                if (ws == 4) best = min(best, shflXor64(best, 2));
-                if (winOk && (lane & (ws - 1)) == 0) commitWindow<R, STEP>(a, wx, wy, c.o, (int)(best & 0xff));
-            } else {
-                bfly<16>(acc, 1, b0);
-                bfly<8>(acc, 2, b1);
-                bfly<4>(acc, 4, b2);
-                int z0 = (b0 ? 8 : 0) + (b1 ? 4 : 0) + (b2 ? 2 : 0);
-                const int lwin = ((cv0 - V0) >> wsLog2) * nwu + (lane >> wsLog2);
-                if (ws == 8) {
-                    atomicAdd(&s_sums[lwin][z0], acc[0]);
-                    atomicAdd(&s_sums[lwin][z0 + 1], acc[1]);
-                } else {  // ws == 16
-                    bfly<2>(acc, 8, b3);
-                    z0 += b3 ? 1 : 0;
-                    atomicAdd(&s_sums[lwin][z0], acc[0]);
-                }
+            best = min(best, shflXor64(best, 1));
+            if (ws == 4) best = min(best, shflXor64(best, 2));
+            if (winOk && (lane & (ws - 1)) == 0) commitWindow<R, STEP>(a, wx, wy, c.o, (int)(best & 0xff));
+        } else {
+            bfly<16>(acc, 1, b0);
+            bfly<8>(acc, 2, b1);
+            bfly<4>(acc, 4, b2);
+            int z0 = (b0 ? 8 : 0) + (b1 ? 4 : 0) + (b2 ? 2 : 0);
+            const int lwin = ((cv0 - V0) >> wsLog2) * nwu + (lane >> wsLog2);
+            if (ws == 8) {
+                atomicAdd(&s_sums[lwin][z0], acc[0]);
+                atomicAdd(&s_sums[lwin][z0 + 1], acc[1]);
+            } else {  // ws == 16
+                bfly<2>(acc, 8, b3);
+                z0 += b3 ? 1 : 0;
+                atomicAdd(&s_sums[lwin][z0], acc[0]);
             }
         }
     }

@@ -57,6 +57,17 @@ __device__ __forceinline__ const uint32_t* rowPtr(const uint32_t* base, int pitc
     return reinterpret_cast<const uint32_t*>(r);
 }
 
+// 16-byte asynchronous copy global -> shared (LDGSTS): no register staging, so a thread keeps all its copies in
+// flight at once; completed by cpAsyncWaitAll() + a barrier.
+__device__ __forceinline__ void cpAsync16(void* smemDst, const void* gmemSrc) {
+    const unsigned d = (unsigned)__cvta_generic_to_shared(smemDst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gmemSrc) : "memory");
+}
+__device__ __forceinline__ void cpAsyncWaitAll() {
+    asm volatile("cp.async.commit_group;" ::: "memory");
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+}
+
 struct WindowCtx {
     int o;          // current offset of the window along the axis of this step
     uint32_t nw;    // in-range flow pixels of the window
