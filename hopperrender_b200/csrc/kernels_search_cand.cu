@@ -18,17 +18,30 @@ namespace hrb {
 
 namespace {
 
-constexpr int CT_U = 32, CT_V = 64;   // tile
-constexpr int SP = 52;                // staged row pitch in words (48 + alignment slack, 13 x 16 B)
-constexpr int RV_MAX = 192;           // staged rows
-constexpr int RU_MAX = 48;            // staged columns actually addressed
+constexpr int CT_U = 32, CT_V = 128;  // tile
+constexpr int SP = 52;                 // staged row pitch in words (48 + alignment slack, 13 x 16 B)
+constexpr int RV_MAX = 256;            // staged rows: 128 + (HI-LO <= 113) + spread_v (<= 15)
+constexpr int RU_MAX = 48;             // staged columns actually addressed
+constexpr int MAX_WIN = (CT_U / 2) * (CT_V / 2);  // windows of a tile at ws = 2
+constexpr int MAX_SUMWIN = (CT_U / 8) * (CT_V / 8);
+constexpr size_t CAND_SMEM = (size_t)RV_MAX * SP * 4 + MAX_SUMWIN * 16 * 4 + MAX_WIN * 4 + 16;
 
-template <int R, int STEP> __global__ void __launch_bounds__(256) sadCandKernel(const SearchArgs a) {
+// lean per-layer total for the in-register finalize: same arithmetic as windowTotal
+template <int R> __device__ __forceinline__ uint32_t layerTotal(const SearchArgs& a, const WindowCtx& c, uint32_t sad, int z) {
+    const int d = z - R / 2;
+    const int cand = (int)(short)(c.o + d * abs(d));
+    uint32_t bias = (uint32_t)abs(cand);
+    if (c.useNb) bias += __sad(c.nb[0], cand, __sad(c.nb[1], cand, __sad(c.nb[2], cand, __sad(c.nb[3], cand, 0u)))) << a.neighborBiasScalar;
+    return (sad << a.deltaScalar) + c.nw * bias;
+}
+
+template <int R, int STEP, bool TAPS> __global__ void __launch_bounds__(256) sadCandKernel(const SearchArgs a) {
     constexpr int LO = candOffset<R>(0), HI = candOffset<R>(R - 1), SPAN = HI - LO;
-    __shared__ __align__(16) uint32_t s_f1[RV_MAX * SP];
-    __shared__ uint32_t s_sums[32][16];  // [window inside the tile][layer] (ws 8: 4 x 8 windows, ws 16: 2 x 4)
-    __shared__ int s_off[512];           // per window of the tile: (ou & 0xffff) | (ov << 16)
-    __shared__ int s_rng[4];             // min ou, max ou, min ov, max ov
+    extern __shared__ __align__(16) uint32_t smem[];
+    uint32_t* __restrict__ s_f1 = smem;                                        // [RV_MAX][SP]
+    uint32_t (*s_sums)[16] = reinterpret_cast<uint32_t (*)[16]>(smem + RV_MAX * SP);  // [window inside the tile][layer] (ws 8, 16)
+    int* __restrict__ s_off = reinterpret_cast<int*>(smem + RV_MAX * SP + MAX_SUMWIN * 16);  // per window: (ou & 0xffff) | (ov << 16)
+    int* __restrict__ s_rng = s_off + MAX_WIN;                                 // min ou, max ou, min ov, max ov
 
     const View<STEP> vw(a);
     const int lane = threadIdx.x, warp = threadIdx.y;
@@ -39,7 +52,7 @@ template <int R, int STEP> __global__ void __launch_bounds__(256) sadCandKernel(
 
     // ---- A. offsets of the tile's windows, and their range ------------------------------------------------------
     if (tid < 4) s_rng[tid] = (tid & 1) ? INT_MIN : INT_MAX;
-    for (int i = tid; i < 32 * 16; i += 256) s_sums[0][i] = 0;
+    for (int i = tid; i < MAX_SUMWIN * 16; i += 256) s_sums[0][i] = 0;
     __syncthreads();
     {
         int mnU = INT_MAX, mxU = INT_MIN, mnV = INT_MAX, mxV = INT_MIN;
@@ -64,7 +77,8 @@ template <int R, int STEP> __global__ void __launch_bounds__(256) sadCandKernel(
     }
     __syncthreads();
     const int minOu = s_rng[0], minOv = s_rng[2];
-    const int RU = CT_U + (s_rng[1] - minOu), RV = CT_V + SPAN + (s_rng[3] - minOv);
+    const int tileRows = min(CT_V, vw.lv - V0);  // flow rows of this tile that exist
+    const int RU = CT_U + (s_rng[1] - minOu), RV = tileRows + SPAN + (s_rng[3] - minOv);
     const bool staged = RU <= RU_MAX && RV <= RV_MAX;  // CTA-uniform
 
     // ---- B. stage the frame-1 region ------------------------------------------------------------------------------
@@ -91,15 +105,15 @@ template <int R, int STEP> __global__ void __launch_bounds__(256) sadCandKernel(
     __syncthreads();
 
     // ---- C. SADs, reduction per window ----------------------------------------------------------------------------
-    // a warp owns 8 consecutive v; they are accumulated in groups of min(ws, 8) rows (one window row each) before the
-    // lanes are reduced, so the reduction is paid once per 8 rows for ws >= 8
+    // a warp owns 16 consecutive v; they are accumulated in groups of min(ws, 16) rows (one window row each) before the
+    // lanes are reduced, so the reduction is paid once per window row
     const bool small = ws <= 4;
     const int cu = U0 + lane;
-    const int gh = ws < 8 ? ws : 8;
+    const int gh = ws < 16 ? ws : 16;
     const bool b0 = lane & 1, b1 = lane & 2, b2 = lane & 4, b3 = lane & 8;
 #pragma unroll 1
-    for (int g = 0; g < 8; g += gh) {
-        const int cv0 = V0 + warp * 8 + g;
+    for (int g = 0; g < 16; g += gh) {
+        const int cv0 = V0 + warp * 16 + g;
         const int wu = cu >> wsLog2, wv = cv0 >> wsLog2;
         const int wx = View<STEP>::wx(wu, wv), wy = View<STEP>::wy(wu, wv);
         const bool pixOk = cu < vw.lu && cv0 < vw.lv;
@@ -115,14 +129,19 @@ template <int R, int STEP> __global__ void __launch_bounds__(256) sadCandKernel(
                 // word index of (row cv0 + ov + LO, column cu + ou) inside the staged region
                 const uint32_t* __restrict__ q = &s_f1[(cv0 - V0 + ov - minOv) * SP + (lane + ou - minOu + sh)];
                 const uint32_t* __restrict__ p2 = rowPtr(vw.p2 + cu, vw.pitch, cv0);
-                uint32_t f2r[8];  // all frame-2 loads of the group are issued before the first one is consumed
 #pragma unroll
-                for (int r = 0; r < 8; ++r) f2r[r] = (r < gh && cv0 + r < vw.lv) ? __ldg(rowPtr(p2, vw.pitch, r)) : 0u;
+                for (int r0 = 0; r0 < 16; r0 += 4) {
+                    if (r0 < gh) {
+                        uint32_t f2r[4];  // the frame-2 loads of four rows are issued before the first one is consumed
 #pragma unroll
-                for (int r = 0; r < 8; ++r) {
-                    if (r < gh && cv0 + r < vw.lv) {
+                        for (int r = 0; r < 4; ++r) f2r[r] = (r0 + r < gh && cv0 + r0 + r < vw.lv) ? __ldg(rowPtr(p2, vw.pitch, r0 + r)) : 0u;
 #pragma unroll
-                        for (int z = 0; z < R; ++z) acc[z] = sad4(q[(r + candOffset<R>(z) - LO) * SP], f2r[r], acc[z]);
+                        for (int r = 0; r < 4; ++r) {
+                            if (r0 + r < gh && cv0 + r0 + r < vw.lv) {
+#pragma unroll
+                                for (int z = 0; z < R; ++z) acc[z] = sad4(q[(r0 + r + candOffset<R>(z) - LO) * SP], f2r[r], acc[z]);
+                            }
+                        }
                     }
                 }
             } else {
@@ -138,6 +157,7 @@ template <int R, int STEP> __global__ void __launch_bounds__(256) sadCandKernel(
         }
 
         if (small) {
+            // windows of 2 or 4 lanes: reduce inside the segment; every lane then finalizes a slice of the layers
             bfly<16>(acc, 1, b0);
             int n = 8, zbase = b0 ? 8 : 0;
             if (ws == 4) {
@@ -147,22 +167,35 @@ template <int R, int STEP> __global__ void __launch_bounds__(256) sadCandKernel(
             }
             WindowCtx c;
             c.o = 0;
-            if (winOk) c = loadWindowCtx<STEP>(a, wx, wy, ox, oy);
-            unsigned long long best = ~0ull;
+            uint32_t bestT = 0xffffffffu;
+            int bestZ = 0xff;
             if (winOk) {
+                c = loadWindowCtx<STEP>(a, wx, wy, ox, oy);
 #pragma unroll
                 for (int i = 0; i < 8; ++i) {
                     const int z = zbase + i;
                     if (i < n && z < R) {
-                        const uint32_t total = windowTotal<R>(a, c, acc[i], z);
-                        tapTotal<R>(a, wx, wy, z, total);
-                        best = min(best, layerKey(total, z));
+                        const uint32_t total = layerTotal<R>(a, c, acc[i], z);
+                        if (TAPS) tapTotal<R>(a, wx, wy, z, total);
+                        if (total < bestT || bestZ == 0xff) {  // z ascends inside a lane: strict < keeps the lowest layer of a tie
+                            bestT = total;
+                            bestZ = z;
+                        }
                     }
                 }
             }
+            unsigned long long best = layerKey(bestT, bestZ);
             best = min(best, shflXor64(best, 1));
             if (ws == 4) best = min(best, shflXor64(best, 2));
-            if (winOk && (lane & (ws - 1)) == 0) commitWindow<R, STEP>(a, wx, wy, c.o, (int)(best & 0xff));
+            if (winOk && (lane & (ws - 1)) == 0) {
+                const int bestLayer = (int)(best & 0xff);
+                const int16_t nOff = (int16_t)(c.o + signedSquare(bestLayer - R / 2));
+                if (STEP == 0)
+                    a.curX[wy * a.nWx + wx] = nOff;
+                else
+                    a.curY[wy * a.nWx + wx] = nOff;
+                if (TAPS && a.tapLayer) a.tapLayer[wy * a.nWx + wx] = (uint8_t)bestLayer;
+            }
         } else {
             bfly<16>(acc, 1, b0);
             bfly<8>(acc, 2, b1);
@@ -190,16 +223,23 @@ template <int R, int STEP> __global__ void __launch_bounds__(256) sadCandKernel(
     }
 }
 
-template <int R> int launchCandR(hrb_ofc* h, const SearchArgs& a, int step) {
-    const dim3 block(32, 8, 1);
-    const int lu = step == 1 ? a.lw : a.lh, lv = step == 1 ? a.lh : a.lw;
+template <int R, int STEP, bool TAPS> int launchCandOne(hrb_ofc* h, const SearchArgs& a) {
+    static bool configured = false;
+    if (!configured) {
+        HRB_CUDA(cudaFuncSetAttribute(sadCandKernel<R, STEP, TAPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CAND_SMEM));
+        configured = true;
+    }
+    const int lu = STEP == 1 ? a.lw : a.lh, lv = STEP == 1 ? a.lh : a.lw;
     const dim3 grid((lu + CT_U - 1) / CT_U, (lv + CT_V - 1) / CT_V, 1);
-    if (step == 1)
-        sadCandKernel<R, 1><<<grid, block, 0, h->stream>>>(a);
-    else
-        sadCandKernel<R, 0><<<grid, block, 0, h->stream>>>(a);
+    sadCandKernel<R, STEP, TAPS><<<grid, dim3(32, 8, 1), CAND_SMEM, h->stream>>>(a);
     HRB_LAUNCH_CHECK();
     return HRB_OK;
+}
+
+template <int R> int launchCandR(hrb_ofc* h, const SearchArgs& a, int step) {
+    const bool taps = a.tapSums || a.tapLayer || a.rawDelta;
+    if (step == 1) return taps ? launchCandOne<R, 1, true>(h, a) : launchCandOne<R, 1, false>(h, a);
+    return taps ? launchCandOne<R, 0, true>(h, a) : launchCandOne<R, 0, false>(h, a);
 }
 
 }  // namespace
