@@ -175,6 +175,7 @@ static int enqueueFlow(hrb_ofc* h) {
     a.deltaScalar = h->deltaScalar;
     a.neighborBiasScalar = h->neighborBiasScalar;
     a.winSums = h->winSums;
+    a.winTicket = h->winTicket;
 
     int prevNWx = 0, prevNWy = 0;
     for (int iter = 0; iter < iterations; ++iter) {
@@ -436,6 +437,7 @@ int hrb_ofc_create(hrb_ofc** out, const hrb_ofc_desc* d) {
     h->stripeY1 = d->frame_height;
     h->levelOffsets[0][0] = h->levelOffsets[0][1] = h->levelOffsets[1][0] = h->levelOffsets[1][1] = nullptr;
     h->winSums = nullptr;
+    h->winTicket = nullptr;
     h->offsetArrayScratch = nullptr;
     h->blurredOffsetArray[0] = h->blurredOffsetArray[1] = nullptr;
     h->flowMaxDev[0] = h->flowMaxDev[1] = nullptr;
@@ -526,6 +528,9 @@ int hrb_ofc_create(hrb_ofc** out, const hrb_ofc_desc* d) {
             HRB_TRY(cudaMemsetAsync(h->levelOffsets[p][ax], 0, h->levelCapacity * sizeof(int16_t), h->stream));
         }
     HRB_TRY(cudaMalloc(&h->winSums, winSumEntries * sizeof(uint32_t)));
+    HRB_TRY(cudaMemsetAsync(h->winSums, 0, winSumEntries * sizeof(uint32_t), h->stream));
+    HRB_TRY(cudaMalloc(&h->winTicket, (winSumEntries / 16 + 1) * sizeof(unsigned)));
+    HRB_TRY(cudaMemsetAsync(h->winTicket, 0, (winSumEntries / 16 + 1) * sizeof(unsigned), h->stream));
     HRB_TRY(cudaMalloc(&h->offsetArrayScratch, 2 * lw * lh * sizeof(int16_t)));
     for (int i = 0; i < 2; ++i) {
         HRB_TRY(cudaMalloc(&h->blurredOffsetArray[i], 2 * lw * lh * sizeof(int16_t)));
@@ -571,6 +576,7 @@ void hrb_ofc_destroy(hrb_ofc* h) {
     for (int p = 0; p < 2; ++p)
         for (int ax = 0; ax < 2; ++ax) cudaFree(h->levelOffsets[p][ax]);
     cudaFree(h->winSums);
+    cudaFree(h->winTicket);
     cudaFree(h->offsetArrayScratch);
     cudaFree(h->blurredOffsetArray[0]);
     cudaFree(h->blurredOffsetArray[1]);
@@ -922,7 +928,7 @@ int hrb_ofc_set_output_stripe(hrb_ofc* h, int row_begin, int row_end) {
 
 int hrb_ofc_set_search_variant(hrb_ofc* h, int variant) {
     HRB_REQUIRE(h, "null handle");
-    HRB_REQUIRE(variant >= 0 && variant <= 2, "variant must be 0 (automatic), 1 (generic kernels only) or 2 (L1-fed sliding kernel)");
+    HRB_REQUIRE(variant >= 0 && variant <= 3, "variant must be 0 (automatic), 1 (generic kernels only), 2 (L1-fed sliding kernel) or 3 (persistent double-buffered sliding kernel)");
     h->searchVariant = variant;
     h->warpVariant = variant == 1 ? 1 : 0;
     return HRB_OK;

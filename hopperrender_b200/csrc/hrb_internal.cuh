@@ -66,6 +66,7 @@ struct SearchArgs {
     int16_t* curX;         // level i offsets: written by step 0, read by step 1
     int16_t* curY;         // level i offsets: written by step 1
     uint32_t* winSums;     // [nW][16] scratch for windows larger than one CTA tile
+    unsigned* winTicket;   // [nW] arrival counters of the sliding kernels' fused finalize (zero between passes)
     uint32_t* rawDelta;    // non-null in pass 0: receives sums[R/2-1][window 0]
     uint32_t* tapSums;     // optional [R][nWy][nWx]
     uint8_t* tapLayer;     // optional [nWy][nWx]
@@ -151,6 +152,7 @@ struct hrb_ofc {
     int16_t* levelOffsets[2][2];   // [iteration parity][axis] window-level offsets
     size_t levelCapacity;          // entries per level array
     uint32_t* winSums;
+    unsigned* winTicket;
     int16_t* offsetArrayScratch;   // [2][lh][lw], materialised on demand for taps
     int16_t* blurredOffsetArray[2];
     uint32_t* flowMaxDev[2];       // max |value| of blurredOffsetArray[i] (rotates with it): lets warpFrames skip the mirror in the interior

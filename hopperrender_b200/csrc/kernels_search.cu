@@ -154,19 +154,24 @@ template <int R> int launchPassR(hrb_ofc* h, const SearchArgs& a, int step, unsi
     const int lu = step == 1 ? a.lw : a.lh, lv = step == 1 ? a.lh : a.lw;  // X steps run on the transposed planes (View)
     const dim3 grid((lu + TILE - 1) / TILE, (lv + TILE - 1) / TILE, 1);
     const bool large = a.ws > TILE;
-    if (large) HRB_CUDA(cudaMemsetAsync(a.winSums, 0, (size_t)a.nWx * a.nWy * 16 * sizeof(uint32_t), h->stream));
     bool done = false;
     if (a.rs == 0 && a.ws <= 16 && h->searchVariant != 1) {  // staged small-window kernel (kernels_search_cand.cu)
         const int rc = launchSearchPassCand(h, a, R, step);
         if (rc > 0) return rc;
         done = rc == HRB_OK;
     }
-    if (a.rs == 0 && a.ws >= 32 && h->searchVariant != 1) {  // sliding-window kernels (kernels_search_big.cu)
+    if (a.rs == 0 && a.ws >= 32 && h->searchVariant != 1) {  // sliding-window kernels (kernels_search_big.cu), finalize fused
         const int rc = launchSearchPassBig(h, a, R, step);
         if (rc > 0) return rc;
-        done = rc == HRB_OK;
+        if (rc == HRB_OK) {
+            *launches = 1;
+            return HRB_OK;
+        }
     }
     if (!done) {
+        // generic kernel; windows larger than its tile go through the scratch sums and a finalize kernel.  The scratch
+        // is zeroed before AND after, because the sliding kernels rely on finding it zeroed.
+        if (large) HRB_CUDA(cudaMemsetAsync(a.winSums, 0, (size_t)a.nWx * a.nWy * 16 * sizeof(uint32_t), h->stream));
         if (step == 0)
             sadPassKernel<R, 0><<<grid, block, 0, h->stream>>>(a);
         else
@@ -181,6 +186,7 @@ template <int R> int launchPassR(hrb_ofc* h, const SearchArgs& a, int step, unsi
         else
             finalizeLargeKernel<R, 1><<<(nW + 127) / 128, 128, 0, h->stream>>>(a);
         HRB_LAUNCH_CHECK();
+        HRB_CUDA(cudaMemsetAsync(a.winSums, 0, (size_t)a.nWx * a.nWy * 16 * sizeof(uint32_t), h->stream));
         *launches = 2;
     }
     return HRB_OK;

@@ -192,7 +192,8 @@ HRB_API int hrb_ofc_set_profile(hrb_ofc* h, int on);
 HRB_API int hrb_ofc_profile_read(hrb_ofc* h, hrb_ofc_profile* out); /* synchronizes */
 HRB_API int hrb_ofc_profile_reset(hrb_ofc* h);
 /* Kernel selection (search ladder and warp): 0 = automatic (specialised kernels where they apply), 1 = the generic
- * kernels for every pass and every warp, 2 = like 0 but the L1-fed instead of the shared-memory-staged sliding kernel.
+ * kernels for every pass and every warp, 2 = like 0 but the L1-fed sliding kernel, 3 = like 0 but the persistent,
+ * double-buffered sliding kernel.
  * Results are identical; exists for A/B measurements and parity tests. */
 HRB_API int hrb_ofc_set_search_variant(hrb_ofc* h, int variant);
 /* number of kernels this library has launched in this process */

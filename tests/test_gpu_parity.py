@@ -115,7 +115,7 @@ SEARCH_CASES = [
 ]
 
 
-@pytest.mark.parametrize("variant", [0, 1, 2], ids=["auto", "generic", "l1slide"])
+@pytest.mark.parametrize("variant", [0, 1, 2, 3], ids=["auto", "generic", "l1slide", "pipelined"])
 @pytest.mark.parametrize("hdr,W,H,maxres,inS,R,kind", SEARCH_CASES)
 def test_search_ladder_taps(synth, hdr, W, H, maxres, inS, R, kind, variant):
     """Every pass of the ladder: window sums, arg-min layers and offsets are bit-exact — with the automatic kernel
