@@ -247,6 +247,61 @@ __global__ void __launch_bounds__(256) blurFlowKernel(const int16_t* __restrict_
     if (threadIdx.x == 0 && (uint32_t)peak > *reinterpret_cast<volatile uint32_t*>(flowMax)) atomicMax(flowMax, (uint32_t)peak);
 }
 
+// Fast path for the usual case — last pass at 2x2 windows, even flow dimensions.  The field is constant on aligned 2x2
+// cells, so the 8 taps of an even output coordinate 2c cover cells c-2..c+1 twice each, and those of an odd coordinate
+// 2c+1 cover c-2 and c+2 once and c-1..c+1 twice; the mirror rule maps to cells unchanged (column -1-p <-> cell -1-c).
+// Both passes therefore run on the cell grid: 5 loads give the two horizontal sums of a cell, 5 more per sum give the
+// four outputs of the cell.  Same integer sums as blurFlowKernel, a sixth of the instructions.
+constexpr int BC_W = 32, BC_H = 16;  // cells per tile -> 64 x 32 outputs
+
+__device__ __forceinline__ int mirrorCell(int c, int n) { return c < 0 ? -c - 1 : (c >= n ? 2 * n - c - 1 : c); }
+__device__ __forceinline__ int div64(int s) { return (s + ((s >> 31) & 63)) >> 6; }  // C division: truncates toward zero
+
+__global__ void __launch_bounds__(256) blurFlowCellKernel(const int16_t* __restrict__ lvlX, const int16_t* __restrict__ lvlY, int nCx, int nCy,
+                                                         int16_t* __restrict__ out, int lw, int lh, uint32_t* __restrict__ flowMax) {
+    __shared__ int16_t s_in[BC_H + 4][BC_W + 4 + 2];
+    __shared__ int s_he[BC_H + 4][BC_W], s_ho[BC_H + 4][BC_W];
+    const int16_t* __restrict__ lvl = blockIdx.z == 0 ? lvlX : lvlY;
+    const int C0 = blockIdx.x * BC_W, R0 = blockIdx.y * BC_H;
+    const int tid = threadIdx.y * 32 + threadIdx.x;
+    for (int i = tid; i < (BC_H + 4) * (BC_W + 4); i += 256) {
+        const int r = i / (BC_W + 4), c = i - r * (BC_W + 4);
+        const int cy = min(mirrorCell(R0 - 2 + r, nCy), nCy - 1), cx = min(mirrorCell(C0 - 2 + c, nCx), nCx - 1);
+        s_in[r][c] = lvl[cy * nCx + cx];
+    }
+    __syncthreads();
+    for (int i = tid; i < (BC_H + 4) * BC_W; i += 256) {
+        const int r = i >> 5, c = i & 31;
+        const int l0 = s_in[r][c], l4 = s_in[r][c + 4];
+        const int mid = s_in[r][c + 1] + s_in[r][c + 2] + s_in[r][c + 3];
+        s_he[r][c] = 2 * (mid + l0);
+        s_ho[r][c] = 2 * mid + l0 + l4;
+    }
+    __syncthreads();
+    int peak = 0;  // largest |flow| this thread wrote: bounds every displacement warpFrames can apply
+    const int cx = C0 + threadIdx.x;
+    if (cx < nCx) {
+        int16_t* __restrict__ o = out + (size_t)blockIdx.z * lw * lh;
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+            const int r = threadIdx.y * 2 + j;
+            const int cy = R0 + r;
+            if (cy >= nCy) break;
+            const int e0 = s_he[r][threadIdx.x], e4 = s_he[r + 4][threadIdx.x];
+            const int em = s_he[r + 1][threadIdx.x] + s_he[r + 2][threadIdx.x] + s_he[r + 3][threadIdx.x];
+            const int o0 = s_ho[r][threadIdx.x], o4 = s_ho[r + 4][threadIdx.x];
+            const int om = s_ho[r + 1][threadIdx.x] + s_ho[r + 2][threadIdx.x] + s_ho[r + 3][threadIdx.x];
+            const int v00 = div64(2 * (em + e0)), v01 = div64(2 * (om + o0));        // row 2cy:   columns 2cx, 2cx+1
+            const int v10 = div64(2 * em + e0 + e4), v11 = div64(2 * om + o0 + o4);  // row 2cy+1
+            *reinterpret_cast<uint32_t*>(o + (size_t)(2 * cy) * lw + 2 * cx) = (uint32_t)(uint16_t)v00 | ((uint32_t)(uint16_t)v01 << 16);
+            *reinterpret_cast<uint32_t*>(o + (size_t)(2 * cy + 1) * lw + 2 * cx) = (uint32_t)(uint16_t)v10 | ((uint32_t)(uint16_t)v11 << 16);
+            peak = max(max(peak, max(abs(v00), abs(v01))), max(abs(v10), abs(v11)));
+        }
+    }
+    peak = __reduce_max_sync(0xffffffffu, peak);
+    if (threadIdx.x == 0 && (uint32_t)peak > *reinterpret_cast<volatile uint32_t*>(flowMax)) atomicMax(flowMax, (uint32_t)peak);
+}
+
 // per-pixel offsetArray [2][lh][lw] from window-level arrays (test taps only)
 __global__ void expandOffsetsKernel(const int16_t* __restrict__ lvlX, int nWxX, int sX, const int16_t* __restrict__ lvlY, int nWxY, int sY,
                                     int16_t* __restrict__ out, int lw, int lh) {
@@ -296,7 +351,12 @@ int launchBlurFlow(hrb_ofc* h, const int16_t* lvlX, const int16_t* lvlY, int nWx
     const dim3 grid((h->flowWidth + BT - 1) / BT, (h->flowHeight + BT - 1) / BT, 2);
     HRB_CUDA(cudaMemsetAsync(flowMax, 0, sizeof(uint32_t), h->stream));
     profBegin(h, CLS_BLUR);
-    blurFlowKernel<<<grid, block, 0, h->stream>>>(lvlX, lvlY, nWx, wsLog2, out, h->flowWidth, h->flowHeight, flowMax);
+    const int lw = h->flowWidth, lh = h->flowHeight;
+    if (wsLog2 == 1 && !(lw & 1) && !(lh & 1) && lw >= 8 && lh >= 8 && nWx == lw / 2 && h->searchVariant != 1) {
+        const dim3 cgrid((lw / 2 + BC_W - 1) / BC_W, (lh / 2 + BC_H - 1) / BC_H, 2);
+        blurFlowCellKernel<<<cgrid, block, 0, h->stream>>>(lvlX, lvlY, lw / 2, lh / 2, out, lw, lh, flowMax);
+    } else
+        blurFlowKernel<<<grid, block, 0, h->stream>>>(lvlX, lvlY, nWx, wsLog2, out, h->flowWidth, h->flowHeight, flowMax);
     HRB_LAUNCH_CHECK();
     profEnd(h, CLS_BLUR, 1);
     return HRB_OK;

@@ -21,11 +21,20 @@ static void* resolve(const char* name) {
         const char* candidates[] = {env, "libOpenCL.so.1", "libnvidia-opencl.so.1", "libOpenCL.so"};
         for (const char* c : candidates) {
             if (!c || !*c) continue;
-            g_lib = dlopen(c, RTLD_NOW | RTLD_LOCAL);
-            if (g_lib) {
-                g_libName = c;
-                break;
+            void* lib = dlopen(c, RTLD_NOW | RTLD_LOCAL);
+            if (!lib) continue;
+            // the ICD loader loads fine without any registered vendor (no /etc/OpenCL/vendors/*.icd) but then reports
+            // no platform: skip it in that case and bind the vendor library directly
+            typedef cl_int (*gp_t)(cl_uint, cl_platform_id*, cl_uint*);
+            gp_t gp = (gp_t)dlsym(lib, "clGetPlatformIDs");
+            cl_uint n = 0;
+            if (!env && gp && (gp(0, nullptr, &n) != CL_SUCCESS || n == 0)) {
+                dlclose(lib);
+                continue;
             }
+            g_lib = lib;
+            g_libName = c;
+            break;
         }
         if (!g_lib) {
             fprintf(stderr, "[hrref] no OpenCL library could be loaded: %s\n", dlerror());
