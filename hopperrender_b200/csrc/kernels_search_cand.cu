@@ -26,17 +26,149 @@ constexpr int MAX_WIN = (CT_U / 2) * (CT_V / 2);  // windows of a tile at ws = 2
 constexpr int MAX_SUMWIN = (CT_U / 8) * (CT_V / 8);
 constexpr size_t CAND_SMEM = (size_t)RV_MAX * SP * 4 + MAX_SUMWIN * 16 * 4 + MAX_WIN * 4 + 16;
 
-// lean per-layer total for the in-register finalize: same arithmetic as windowTotal
-template <int R> __device__ __forceinline__ uint32_t layerTotal(const SearchArgs& a, const WindowCtx& c, uint32_t sad, int z) {
-    const int d = z - R / 2;
-    const int cand = (int)(short)(c.o + d * abs(d));
+// lean per-layer total for the in-register finalize: same arithmetic as windowTotal, candidate offset given
+__device__ __forceinline__ uint32_t layerTotal(const SearchArgs& a, const WindowCtx& c, uint32_t sad, int sq) {
+    const int cand = (int)(short)(c.o + sq);
     uint32_t bias = (uint32_t)abs(cand);
     if (c.useNb) bias += __sad(c.nb[0], cand, __sad(c.nb[1], cand, __sad(c.nb[2], cand, __sad(c.nb[3], cand, 0u)))) << a.neighborBiasScalar;
     return (sad << a.deltaScalar) + c.nw * bias;
 }
 
-template <int R, int STEP, bool TAPS> __global__ void __launch_bounds__(256) sadCandKernel(const SearchArgs a) {
+struct CandTile {
+    const uint32_t* s_f1;
+    uint32_t (*s_sums)[16];
+    const int* s_off;
+    int U0, V0, minOu, minOv, sh;
+    bool staged;
+};
+
+// SADs and per-window reduction of one warp's 16 rows.  A warp accumulates groups of min(WS, 16) rows (one window row
+// each) before the lanes are reduced, so the reduction is paid once per window row.  FULL: the tile lies inside the
+// flow field and is staged, so no pixel needs a range check.
+template <int R, int STEP, bool TAPS, int WS, bool FULL>
+__device__ __forceinline__ void candGroups(const SearchArgs& a, const View<STEP>& vw, const CandTile& t, int lane, int warp) {
+    constexpr int LO = candOffset<R>(0);
+    constexpr int L2 = WS == 2 ? 1 : WS == 4 ? 2 : WS == 8 ? 3 : 4;
+    constexpr int GH = WS < 16 ? WS : 16;
+    constexpr int NWU = CT_U >> L2;
+    const int cu = t.U0 + lane;
+    const bool b0 = lane & 1, b1 = lane & 2, b2 = lane & 4, b3 = lane & 8;
+
+    // layers a lane finalizes for WS <= 4 (what the butterfly leaves it with) and their displacements
+    constexpr int NZ = WS == 2 ? 8 : 4;
+    const int zbase = WS == 2 ? (b0 ? 8 : 0) : (b0 ? 8 : 0) + (b1 ? 4 : 0);
+    int sqv[NZ];
+    if (WS <= 4) {
+#pragma unroll
+        for (int i = 0; i < NZ; ++i) {
+            if (WS == 2)
+                sqv[i] = b0 ? signedSquare(8 + i - R / 2) : signedSquare(i - R / 2);
+            else
+                sqv[i] = b0 ? (b1 ? signedSquare(12 + i - R / 2) : signedSquare(8 + i - R / 2)) : (b1 ? signedSquare(4 + i - R / 2) : signedSquare(i - R / 2));
+        }
+    }
+
+#pragma unroll 1
+    for (int g = 0; g < 16; g += GH) {
+        const int cv0 = t.V0 + warp * 16 + g;
+        const int wu = cu >> L2, wv = cv0 >> L2;
+        const int wx = View<STEP>::wx(wu, wv), wy = View<STEP>::wy(wu, wv);
+        const bool pixOk = FULL || (cu < vw.lu && cv0 < vw.lv);
+        const bool winOk = FULL || ((wu << L2) < vw.lu && cv0 < vw.lv);
+        const int packed = t.s_off[(wv - (t.V0 >> L2)) * NWU + (wu - (t.U0 >> L2))];
+        const int ou = (int)(short)(packed & 0xffff), ov = packed >> 16;
+        const int ox = STEP == 1 ? ou : ov, oy = STEP == 1 ? ov : ou;
+        uint32_t acc[16];
+#pragma unroll
+        for (int z = 0; z < 16; ++z) acc[z] = 0;
+        if (pixOk) {
+            if (FULL || t.staged) {
+                // word index of (row cv0 + ov + LO, column cu + ou) inside the staged region
+                const uint32_t* __restrict__ q = &t.s_f1[(cv0 - t.V0 + ov - t.minOv) * SP + (lane + ou - t.minOu + t.sh)];
+                const uint32_t* __restrict__ p2 = rowPtr(vw.p2 + cu, vw.pitch, cv0);
+                constexpr int RB = GH < 8 ? GH : 8;  // frame-2 rows loaded before the first one is consumed
+#pragma unroll
+                for (int r0 = 0; r0 < GH; r0 += RB) {
+                    uint32_t f2r[RB];
+#pragma unroll
+                    for (int r = 0; r < RB; ++r) f2r[r] = (FULL || cv0 + r0 + r < vw.lv) ? __ldg(rowPtr(p2, vw.pitch, r0 + r)) : 0u;
+#pragma unroll
+                    for (int r = 0; r < RB; ++r) {
+                        if (FULL || cv0 + r0 + r < vw.lv) {
+#pragma unroll
+                            for (int z = 0; z < R; ++z) acc[z] = sad4(q[(r0 + r + candOffset<R>(z) - LO) * SP], f2r[r], acc[z]);
+                        }
+                    }
+                }
+            } else {
+                const uint32_t* __restrict__ col = vw.p1 + mirrorSearch(cu + ou, vw.dimU);
+                for (int r = 0; r < GH; ++r) {
+                    if (cv0 + r >= vw.lv) break;
+                    const uint32_t f2 = __ldg(rowPtr(vw.p2 + cu, vw.pitch, cv0 + r));
+                    const int bv = cv0 + r + ov;
+#pragma unroll
+                    for (int z = 0; z < R; ++z) acc[z] = sad4(__ldg(rowPtr(col, vw.pitch, mirrorSearch(bv + candOffset<R>(z), vw.dimV))), f2, acc[z]);
+                }
+            }
+        }
+
+        if (WS <= 4) {
+            // windows of 2 or 4 lanes: reduce inside the segment; every lane then finalizes a slice of the layers
+            bfly<16>(acc, 1, b0);
+            if (WS == 4) bfly<8>(acc, 2, b1);
+            WindowCtx c;
+            c.o = 0;
+            uint32_t bestT = 0xffffffffu;
+            int bestZ = zbase < R ? zbase : 0xff;  // no layer beats a sum of 2^32-1: the lane's first layer stands, as with strict <
+            if (winOk) {
+                c = loadWindowCtx<STEP>(a, wx, wy, ox, oy);
+#pragma unroll
+                for (int i = 0; i < NZ; ++i) {
+                    const int z = zbase + i;
+                    if (R == 16 || z < R) {
+                        const uint32_t total = layerTotal(a, c, acc[i], sqv[i]);
+                        if (TAPS) tapTotal<R>(a, wx, wy, z, total);
+                        if (total < bestT) {  // z ascends inside a lane: strict < keeps the lowest layer of a tie
+                            bestT = total;
+                            bestZ = z;
+                        }
+                    }
+                }
+            }
+            unsigned long long best = layerKey(bestT, bestZ);
+            best = min(best, shflXor64(best, 1));
+            if (WS == 4) best = min(best, shflXor64(best, 2));
+            if (winOk && (lane & (WS - 1)) == 0) {
+                const int bestLayer = (int)(best & 0xff);
+                const int16_t nOff = (int16_t)(c.o + signedSquare(bestLayer - R / 2));
+                if (STEP == 0)
+                    a.curX[wy * a.nWx + wx] = nOff;
+                else
+                    a.curY[wy * a.nWx + wx] = nOff;
+                if (TAPS && a.tapLayer) a.tapLayer[wy * a.nWx + wx] = (uint8_t)bestLayer;
+            }
+        } else {
+            bfly<16>(acc, 1, b0);
+            bfly<8>(acc, 2, b1);
+            bfly<4>(acc, 4, b2);
+            int z0 = (b0 ? 8 : 0) + (b1 ? 4 : 0) + (b2 ? 2 : 0);
+            const int lwin = ((cv0 - t.V0) >> L2) * NWU + (lane >> L2);
+            if (WS == 8) {
+                atomicAdd(&t.s_sums[lwin][z0], acc[0]);
+                atomicAdd(&t.s_sums[lwin][z0 + 1], acc[1]);
+            } else {  // WS == 16
+                bfly<2>(acc, 8, b3);
+                z0 += b3 ? 1 : 0;
+                atomicAdd(&t.s_sums[lwin][z0], acc[0]);
+            }
+        }
+    }
+}
+
+template <int R, int STEP, bool TAPS, int WS> __global__ void __launch_bounds__(256) sadCandKernel(const SearchArgs a) {
     constexpr int LO = candOffset<R>(0), HI = candOffset<R>(R - 1), SPAN = HI - LO;
+    constexpr int wsLog2 = WS == 2 ? 1 : WS == 4 ? 2 : WS == 8 ? 3 : 4;
+    constexpr int nwu = CT_U >> wsLog2, nwv = CT_V >> wsLog2;  // windows of the tile along u, v
     extern __shared__ __align__(16) uint32_t smem[];
     uint32_t* __restrict__ s_f1 = smem;                                        // [RV_MAX][SP]
     uint32_t (*s_sums)[16] = reinterpret_cast<uint32_t (*)[16]>(smem + RV_MAX * SP);  // [window inside the tile][layer] (ws 8, 16)
@@ -46,28 +178,31 @@ template <int R, int STEP, bool TAPS> __global__ void __launch_bounds__(256) sad
     const View<STEP> vw(a);
     const int lane = threadIdx.x, warp = threadIdx.y;
     const int tid = warp * 32 + lane;
-    const int ws = a.ws, wsLog2 = a.wsLog2;
     const int U0 = blockIdx.x * CT_U, V0 = blockIdx.y * CT_V;
-    const int nwu = CT_U >> wsLog2, nwv = CT_V >> wsLog2;  // windows of the tile along u, v
 
     // ---- A. offsets of the tile's windows, and their range ------------------------------------------------------
     if (tid < 4) s_rng[tid] = (tid & 1) ? INT_MIN : INT_MAX;
-    for (int i = tid; i < MAX_SUMWIN * 16; i += 256) s_sums[0][i] = 0;
+    if (WS >= 8)
+        for (int i = tid; i < nwu * nwv * 16; i += 256) s_sums[0][i] = 0;
     __syncthreads();
     {
         int mnU = INT_MAX, mxU = INT_MIN, mnV = INT_MAX, mxV = INT_MIN;
-        for (int i = tid; i < nwu * nwv; i += 256) {
-            const int lwu = i % nwu, lwv = i / nwu;
-            const int wu = (U0 >> wsLog2) + lwu, wv = (V0 >> wsLog2) + lwv;
-            int packed = 0;
-            if ((wu << wsLog2) < vw.lu && (wv << wsLog2) < vw.lv) {
-                int ox, oy;
-                loadWindowOffsets<STEP>(a, View<STEP>::wx(wu, wv), View<STEP>::wy(wu, wv), ox, oy);
-                const int ou = View<STEP>::ou(ox, oy), ov = View<STEP>::ov(ox, oy);
-                packed = (ou & 0xffff) | (ov << 16);
-                mnU = min(mnU, ou); mxU = max(mxU, ou); mnV = min(mnV, ov); mxV = max(mxV, ov);
+#pragma unroll
+        for (int i0 = 0; i0 < nwu * nwv; i0 += 256) {
+            const int i = i0 + tid;
+            if (nwu * nwv >= 256 || i < nwu * nwv) {
+                const int lwu = i % nwu, lwv = i / nwu;
+                const int wu = (U0 >> wsLog2) + lwu, wv = (V0 >> wsLog2) + lwv;
+                int packed = 0;
+                if ((wu << wsLog2) < vw.lu && (wv << wsLog2) < vw.lv) {
+                    int ox, oy;
+                    loadWindowOffsets<STEP>(a, View<STEP>::wx(wu, wv), View<STEP>::wy(wu, wv), ox, oy);
+                    const int ou = View<STEP>::ou(ox, oy), ov = View<STEP>::ov(ox, oy);
+                    packed = (ou & 0xffff) | (ov << 16);
+                    mnU = min(mnU, ou); mxU = max(mxU, ou); mnV = min(mnV, ov); mxV = max(mxV, ov);
+                }
+                s_off[i] = packed;
             }
-            s_off[i] = packed;
         }
         mnU = __reduce_min_sync(0xffffffffu, mnU); mxU = __reduce_max_sync(0xffffffffu, mxU);
         mnV = __reduce_min_sync(0xffffffffu, mnV); mxV = __reduce_max_sync(0xffffffffu, mxV);
@@ -105,115 +240,15 @@ template <int R, int STEP, bool TAPS> __global__ void __launch_bounds__(256) sad
     __syncthreads();
 
     // ---- C. SADs, reduction per window ----------------------------------------------------------------------------
-    // a warp owns 16 consecutive v; they are accumulated in groups of min(ws, 16) rows (one window row each) before the
-    // lanes are reduced, so the reduction is paid once per window row
-    const bool small = ws <= 4;
-    const int cu = U0 + lane;
-    const int gh = ws < 16 ? ws : 16;
-    const bool b0 = lane & 1, b1 = lane & 2, b2 = lane & 4, b3 = lane & 8;
-#pragma unroll 1
-    for (int g = 0; g < 16; g += gh) {
-        const int cv0 = V0 + warp * 16 + g;
-        const int wu = cu >> wsLog2, wv = cv0 >> wsLog2;
-        const int wx = View<STEP>::wx(wu, wv), wy = View<STEP>::wy(wu, wv);
-        const bool pixOk = cu < vw.lu && cv0 < vw.lv;
-        const bool winOk = (wu << wsLog2) < vw.lu && cv0 < vw.lv;
-        const int packed = s_off[(wv - (V0 >> wsLog2)) * nwu + (wu - (U0 >> wsLog2))];
-        const int ou = (int)(short)(packed & 0xffff), ov = packed >> 16;
-        const int ox = STEP == 1 ? ou : ov, oy = STEP == 1 ? ov : ou;
-        uint32_t acc[16];
-#pragma unroll
-        for (int z = 0; z < 16; ++z) acc[z] = 0;
-        if (pixOk) {
-            if (staged) {
-                // word index of (row cv0 + ov + LO, column cu + ou) inside the staged region
-                const uint32_t* __restrict__ q = &s_f1[(cv0 - V0 + ov - minOv) * SP + (lane + ou - minOu + sh)];
-                const uint32_t* __restrict__ p2 = rowPtr(vw.p2 + cu, vw.pitch, cv0);
-#pragma unroll
-                for (int r0 = 0; r0 < 16; r0 += 4) {
-                    if (r0 < gh) {
-                        uint32_t f2r[4];  // the frame-2 loads of four rows are issued before the first one is consumed
-#pragma unroll
-                        for (int r = 0; r < 4; ++r) f2r[r] = (r0 + r < gh && cv0 + r0 + r < vw.lv) ? __ldg(rowPtr(p2, vw.pitch, r0 + r)) : 0u;
-#pragma unroll
-                        for (int r = 0; r < 4; ++r) {
-                            if (r0 + r < gh && cv0 + r0 + r < vw.lv) {
-#pragma unroll
-                                for (int z = 0; z < R; ++z) acc[z] = sad4(q[(r0 + r + candOffset<R>(z) - LO) * SP], f2r[r], acc[z]);
-                            }
-                        }
-                    }
-                }
-            } else {
-                const uint32_t* __restrict__ col = vw.p1 + mirrorSearch(cu + ou, vw.dimU);
-                for (int r = 0; r < gh; ++r) {
-                    if (cv0 + r >= vw.lv) break;
-                    const uint32_t f2 = __ldg(rowPtr(vw.p2 + cu, vw.pitch, cv0 + r));
-                    const int bv = cv0 + r + ov;
-#pragma unroll
-                    for (int z = 0; z < R; ++z) acc[z] = sad4(__ldg(rowPtr(col, vw.pitch, mirrorSearch(bv + candOffset<R>(z), vw.dimV))), f2, acc[z]);
-                }
-            }
-        }
+    CandTile t;
+    t.s_f1 = s_f1; t.s_sums = s_sums; t.s_off = s_off;
+    t.U0 = U0; t.V0 = V0; t.minOu = minOu; t.minOv = minOv; t.sh = sh; t.staged = staged;
+    if (staged && U0 + CT_U <= vw.lu && V0 + CT_V <= vw.lv)
+        candGroups<R, STEP, TAPS, WS, true>(a, vw, t, lane, warp);
+    else
+        candGroups<R, STEP, TAPS, WS, false>(a, vw, t, lane, warp);
 
-        if (small) {
-            // windows of 2 or 4 lanes: reduce inside the segment; every lane then finalizes a slice of the layers
-            bfly<16>(acc, 1, b0);
-            int n = 8, zbase = b0 ? 8 : 0;
-            if (ws == 4) {
-                bfly<8>(acc, 2, b1);
-                n = 4;
-                zbase += b1 ? 4 : 0;
-            }
-            WindowCtx c;
-            c.o = 0;
-            uint32_t bestT = 0xffffffffu;
-            int bestZ = 0xff;
-            if (winOk) {
-                c = loadWindowCtx<STEP>(a, wx, wy, ox, oy);
-#pragma unroll
-                for (int i = 0; i < 8; ++i) {
-                    const int z = zbase + i;
-                    if (i < n && z < R) {
-                        const uint32_t total = layerTotal<R>(a, c, acc[i], z);
-                        if (TAPS) tapTotal<R>(a, wx, wy, z, total);
-                        if (total < bestT || bestZ == 0xff) {  // z ascends inside a lane: strict < keeps the lowest layer of a tie
-                            bestT = total;
-                            bestZ = z;
-                        }
-                    }
-                }
-            }
-            unsigned long long best = layerKey(bestT, bestZ);
-            best = min(best, shflXor64(best, 1));
-            if (ws == 4) best = min(best, shflXor64(best, 2));
-            if (winOk && (lane & (ws - 1)) == 0) {
-                const int bestLayer = (int)(best & 0xff);
-                const int16_t nOff = (int16_t)(c.o + signedSquare(bestLayer - R / 2));
-                if (STEP == 0)
-                    a.curX[wy * a.nWx + wx] = nOff;
-                else
-                    a.curY[wy * a.nWx + wx] = nOff;
-                if (TAPS && a.tapLayer) a.tapLayer[wy * a.nWx + wx] = (uint8_t)bestLayer;
-            }
-        } else {
-            bfly<16>(acc, 1, b0);
-            bfly<8>(acc, 2, b1);
-            bfly<4>(acc, 4, b2);
-            int z0 = (b0 ? 8 : 0) + (b1 ? 4 : 0) + (b2 ? 2 : 0);
-            const int lwin = ((cv0 - V0) >> wsLog2) * nwu + (lane >> wsLog2);
-            if (ws == 8) {
-                atomicAdd(&s_sums[lwin][z0], acc[0]);
-                atomicAdd(&s_sums[lwin][z0 + 1], acc[1]);
-            } else {  // ws == 16
-                bfly<2>(acc, 8, b3);
-                z0 += b3 ? 1 : 0;
-                atomicAdd(&s_sums[lwin][z0], acc[0]);
-            }
-        }
-    }
-
-    if (!small) {
+    if (WS >= 8) {
         __syncthreads();
         if (tid < nwu * nwv) {
             const int wu = (U0 >> wsLog2) + (tid % nwu), wv = (V0 >> wsLog2) + (tid / nwu);
@@ -223,23 +258,33 @@ template <int R, int STEP, bool TAPS> __global__ void __launch_bounds__(256) sad
     }
 }
 
-template <int R, int STEP, bool TAPS> int launchCandOne(hrb_ofc* h, const SearchArgs& a) {
+template <int R, int STEP, bool TAPS, int WS> int launchCandOne(hrb_ofc* h, const SearchArgs& a) {
     static bool configured = false;
     if (!configured) {
-        HRB_CUDA(cudaFuncSetAttribute(sadCandKernel<R, STEP, TAPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CAND_SMEM));
+        HRB_CUDA(cudaFuncSetAttribute(sadCandKernel<R, STEP, TAPS, WS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CAND_SMEM));
         configured = true;
     }
     const int lu = STEP == 1 ? a.lw : a.lh, lv = STEP == 1 ? a.lh : a.lw;
     const dim3 grid((lu + CT_U - 1) / CT_U, (lv + CT_V - 1) / CT_V, 1);
-    sadCandKernel<R, STEP, TAPS><<<grid, dim3(32, 8, 1), CAND_SMEM, h->stream>>>(a);
+    sadCandKernel<R, STEP, TAPS, WS><<<grid, dim3(32, 8, 1), CAND_SMEM, h->stream>>>(a);
     HRB_LAUNCH_CHECK();
     return HRB_OK;
 }
 
+template <int R, int STEP, bool TAPS> int launchCandWs(hrb_ofc* h, const SearchArgs& a) {
+    switch (a.ws) {
+        case 2: return launchCandOne<R, STEP, TAPS, 2>(h, a);
+        case 4: return launchCandOne<R, STEP, TAPS, 4>(h, a);
+        case 8: return launchCandOne<R, STEP, TAPS, 8>(h, a);
+        case 16: return launchCandOne<R, STEP, TAPS, 16>(h, a);
+        default: return -1;
+    }
+}
+
 template <int R> int launchCandR(hrb_ofc* h, const SearchArgs& a, int step) {
     const bool taps = a.tapSums || a.tapLayer || a.rawDelta;
-    if (step == 1) return taps ? launchCandOne<R, 1, true>(h, a) : launchCandOne<R, 1, false>(h, a);
-    return taps ? launchCandOne<R, 0, true>(h, a) : launchCandOne<R, 0, false>(h, a);
+    if (step == 1) return taps ? launchCandWs<R, 1, true>(h, a) : launchCandWs<R, 1, false>(h, a);
+    return taps ? launchCandWs<R, 0, true>(h, a) : launchCandWs<R, 0, false>(h, a);
 }
 
 }  // namespace
