@@ -155,12 +155,12 @@ template <int R> int launchPassR(hrb_ofc* h, const SearchArgs& a, int step, unsi
     const dim3 grid((lu + TILE - 1) / TILE, (lv + TILE - 1) / TILE, 1);
     const bool large = a.ws > TILE;
     bool done = false;
-    if (a.rs == 0 && a.ws <= 16 && h->searchVariant != 1) {  // staged small-window kernel (kernels_search_cand.cu)
+    if (a.rs == 0 && a.ws <= (h->searchVariant == 0 ? 32 : 16) && h->searchVariant != 1) {  // staged small-window kernel (kernels_search_cand.cu)
         const int rc = launchSearchPassCand(h, a, R, step);
         if (rc > 0) return rc;
         done = rc == HRB_OK;
     }
-    if (a.rs == 0 && a.ws >= 32 && h->searchVariant != 1) {  // sliding-window kernels (kernels_search_big.cu), finalize fused
+    if (!done && a.rs == 0 && a.ws >= 32 && h->searchVariant != 1) {  // sliding-window kernels (kernels_search_big.cu), finalize fused
         const int rc = launchSearchPassBig(h, a, R, step);
         if (rc > 0) return rc;
         if (rc == HRB_OK) {

@@ -48,7 +48,7 @@ struct CandTile {
 template <int R, int STEP, bool TAPS, int WS, bool FULL>
 __device__ __forceinline__ void candGroups(const SearchArgs& a, const View<STEP>& vw, const CandTile& t, int lane, int warp) {
     constexpr int LO = candOffset<R>(0);
-    constexpr int L2 = WS == 2 ? 1 : WS == 4 ? 2 : WS == 8 ? 3 : 4;
+    constexpr int L2 = WS == 2 ? 1 : WS == 4 ? 2 : WS == 8 ? 3 : WS == 16 ? 4 : 5;
     constexpr int GH = WS < 16 ? WS : 16;
     constexpr int NWU = CT_U >> L2;
     const int cu = t.U0 + lane;
@@ -156,10 +156,14 @@ __device__ __forceinline__ void candGroups(const SearchArgs& a, const View<STEP>
             if (WS == 8) {
                 atomicAdd(&t.s_sums[lwin][z0], acc[0]);
                 atomicAdd(&t.s_sums[lwin][z0 + 1], acc[1]);
-            } else {  // WS == 16
+            } else {  // WS == 16, 32
                 bfly<2>(acc, 8, b3);
                 z0 += b3 ? 1 : 0;
-                atomicAdd(&t.s_sums[lwin][z0], acc[0]);
+                if (WS == 32) {
+                    acc[0] += __shfl_xor_sync(0xffffffffu, acc[0], 16);
+                    if (lane < 16) atomicAdd(&t.s_sums[lwin][z0], acc[0]);
+                } else
+                    atomicAdd(&t.s_sums[lwin][z0], acc[0]);
             }
         }
     }
@@ -167,7 +171,7 @@ __device__ __forceinline__ void candGroups(const SearchArgs& a, const View<STEP>
 
 template <int R, int STEP, bool TAPS, int WS> __global__ void __launch_bounds__(256) sadCandKernel(const SearchArgs a) {
     constexpr int LO = candOffset<R>(0), HI = candOffset<R>(R - 1), SPAN = HI - LO;
-    constexpr int wsLog2 = WS == 2 ? 1 : WS == 4 ? 2 : WS == 8 ? 3 : 4;
+    constexpr int wsLog2 = WS == 2 ? 1 : WS == 4 ? 2 : WS == 8 ? 3 : WS == 16 ? 4 : 5;
     constexpr int nwu = CT_U >> wsLog2, nwv = CT_V >> wsLog2;  // windows of the tile along u, v
     extern __shared__ __align__(16) uint32_t smem[];
     uint32_t* __restrict__ s_f1 = smem;                                        // [RV_MAX][SP]
@@ -277,6 +281,7 @@ template <int R, int STEP, bool TAPS> int launchCandWs(hrb_ofc* h, const SearchA
         case 4: return launchCandOne<R, STEP, TAPS, 4>(h, a);
         case 8: return launchCandOne<R, STEP, TAPS, 8>(h, a);
         case 16: return launchCandOne<R, STEP, TAPS, 16>(h, a);
+        case 32: return launchCandOne<R, STEP, TAPS, 32>(h, a);
         default: return -1;
     }
 }
@@ -289,7 +294,7 @@ template <int R> int launchCandR(hrb_ofc* h, const SearchArgs& a, int step) {
 
 }  // namespace
 
-// One whole pass (SAD + arg-min + offset update) for 2 <= ws <= 16 at full flow resolution.
+// One whole pass (SAD + arg-min + offset update) for 2 <= ws <= 32 at full flow resolution.
 int launchSearchPassCand(hrb_ofc* h, const SearchArgs& a, int R, int step) {
     switch (R) {
 #define HRB_CASE(N) case N: return launchCandR<N>(h, a, step);
