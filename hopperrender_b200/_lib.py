@@ -79,6 +79,8 @@ PROTOTYPES = {
     "hrb_ofc_profile_read": (C.c_int, [_P, C.POINTER(hrb_ofc_profile)]),
     "hrb_ofc_profile_reset": (C.c_int, [_P]),
     "hrb_ofc_set_search_variant": (C.c_int, [_P, C.c_int]),
+    "hrb_ofc_set_flow_overlap": (C.c_int, [_P, C.c_int]),
+    "hrb_ofc_join_flow": (C.c_int, [_P]),
     "hrb_kernel_launch_count": (C.c_uint64, []),
     "hrb_microbench_sad_peak": (C.c_int, [C.c_int, C.POINTER(C.c_double)]),
     "hrb_last_error": (C.c_char_p, []),

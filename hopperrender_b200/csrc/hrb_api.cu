@@ -429,7 +429,8 @@ int hrb_ofc_create(hrb_ofc** out, const hrb_ofc_desc* d) {
         h->outReady[i] = h->outFree[i] = nullptr;
     }
     for (auto& e : h->ticketEvent) e = nullptr;
-    h->upStream = h->downStream = nullptr;
+    h->upStream = h->downStream = h->flowStream = nullptr;
+    h->flowForkEvent = h->flowJoinEvent = nullptr;
     h->spareFreeEvent = nullptr;
     h->outCur = h->outView = 0;
     h->downloadSeq = 0;
@@ -505,6 +506,11 @@ int hrb_ofc_create(hrb_ofc** out, const hrb_ofc_desc* d) {
     HRB_TRY(cudaEventCreate(&h->warpEndEvent));
     HRB_TRY(cudaEventCreateWithFlags(&h->uploadDoneEvent, cudaEventBlockingSync | cudaEventDisableTiming));
     HRB_TRY(cudaStreamCreateWithFlags(&h->upStream, cudaStreamNonBlocking));
+    HRB_TRY(cudaStreamCreateWithFlags(&h->flowStream, cudaStreamNonBlocking));
+    HRB_TRY(cudaEventCreateWithFlags(&h->flowForkEvent, cudaEventDisableTiming));
+    HRB_TRY(cudaEventCreateWithFlags(&h->flowJoinEvent, cudaEventDisableTiming));
+    h->flowJoinPending = false;
+    h->flowOverlap = true;
     HRB_TRY(cudaStreamCreateWithFlags(&h->downStream, cudaStreamNonBlocking));
     HRB_TRY(cudaEventCreateWithFlags(&h->spareFreeEvent, cudaEventDisableTiming));
     for (int i = 0; i < hrb_ofc::kOutRing; ++i) {
@@ -551,6 +557,7 @@ void hrb_ofc_destroy(hrb_ofc* h) {
     cudaSetDevice(h->device);
     if (h->stream) cudaStreamSynchronize(h->stream);  // clFinish, opticalFlowCalcSDR.cpp:186
     if (h->upStream) cudaStreamSynchronize(h->upStream);
+    if (h->flowStream) cudaStreamSynchronize(h->flowStream);
     if (h->downStream) cudaStreamSynchronize(h->downStream);
     freeTaps(h);
     for (auto& p : h->prof.pending) {
@@ -572,6 +579,9 @@ void hrb_ofc_destroy(hrb_ofc* h) {
         if (e) cudaEventDestroy(e);
     if (h->spareFreeEvent) cudaEventDestroy(h->spareFreeEvent);
     if (h->upStream) cudaStreamDestroy(h->upStream);
+    if (h->flowStream) cudaStreamDestroy(h->flowStream);
+    if (h->flowForkEvent) cudaEventDestroy(h->flowForkEvent);
+    if (h->flowJoinEvent) cudaEventDestroy(h->flowJoinEvent);
     if (h->downStream) cudaStreamDestroy(h->downStream);
     for (int p = 0; p < 2; ++p)
         for (int ax = 0; ax < 2; ++ax) cudaFree(h->levelOffsets[p][ax]);
@@ -620,14 +630,44 @@ int hrb_ofc_update_frame_device(hrb_ofc* h, const void* device_planes) {
     return finishUpdate(h);
 }
 
+// Orders the compute stream behind the last flow calculation that was enqueued on the flow stream.
+static int joinFlow(hrb_ofc* h) {
+    if (h->flowJoinPending) {
+        HRB_CUDA(cudaSetDevice(h->device));
+        HRB_CUDA(cudaStreamWaitEvent(h->stream, h->flowJoinEvent, 0));
+        h->flowJoinPending = false;
+    }
+    return HRB_OK;
+}
+
+// warpFrames reads the flow of the PREVIOUS calculation (m_blurredOffsetArray12[0] after the swap,
+// opticalFlowCalcSDR.cpp:113-123,150) and the search touches nothing the warp writes, so the calculation of source
+// frame N and the warps issued after it are independent: the asynchronous entry point runs the search ladder on its
+// own stream, forked behind everything already enqueued (the ingest of frame N, the last readers of the flow buffer
+// it overwrites) and joined before the next calculation — i.e. before any warp that needs its result.
 int hrb_ofc_calculate_optical_flow_async(hrb_ofc* h) {
     HRB_REQUIRE(h, "null handle");
-    return enqueueFlow(h);
+    int rc = joinFlow(h);
+    if (rc) return rc;
+    if (!h->flowOverlap || h->tapMode || h->prof.on) return enqueueFlow(h);
+    HRB_CUDA(cudaSetDevice(h->device));
+    HRB_CUDA(cudaEventRecord(h->flowForkEvent, h->stream));
+    HRB_CUDA(cudaStreamWaitEvent(h->flowStream, h->flowForkEvent, 0));
+    cudaStream_t compute = h->stream;
+    h->stream = h->flowStream;
+    rc = enqueueFlow(h);
+    h->stream = compute;
+    if (rc) return rc;
+    HRB_CUDA(cudaEventRecord(h->flowJoinEvent, h->flowStream));
+    h->flowJoinPending = true;
+    return HRB_OK;
 }
 
 int hrb_ofc_calculate_optical_flow(hrb_ofc* h) {
     HRB_REQUIRE(h, "null handle");
-    const int rc = enqueueFlow(h);
+    int rc = joinFlow(h);
+    if (rc) return rc;
+    rc = enqueueFlow(h);
     if (rc) return rc;
     return resolveFlow(h);
 }
@@ -690,8 +730,10 @@ int hrb_ofc_synchronize(hrb_ofc* h) {
     HRB_REQUIRE(h, "null handle");
     HRB_CUDA(cudaSetDevice(h->device));
     HRB_CUDA(cudaStreamSynchronize(h->upStream));
+    HRB_CUDA(cudaStreamSynchronize(h->flowStream));
     HRB_CUDA(cudaStreamSynchronize(h->stream));
     HRB_CUDA(cudaStreamSynchronize(h->downStream));
+    h->flowJoinPending = false;
     return resolveFlow(h);
 }
 
@@ -777,6 +819,7 @@ int hrb_ofc_reset(hrb_ofc* h) { return hrb_ofc_set_frame_count(h, 0); }
 int hrb_ofc_set_tap_mode(hrb_ofc* h, int on) {
     HRB_REQUIRE(h, "null handle");
     HRB_CUDA(cudaSetDevice(h->device));
+    if (joinFlow(h)) return HRB_ERR_CUDA;
     HRB_CUDA(cudaStreamSynchronize(h->stream));
     h->tapMode = on != 0;
     if (!h->tapMode) freeTaps(h);
@@ -833,6 +876,7 @@ int hrb_ofc_read_pass_tap(hrb_ofc* h, int pass, int which, void* dst, size_t byt
 int hrb_ofc_read_buffer(hrb_ofc* h, int which, void* dst, size_t bytes) {
     HRB_REQUIRE(h && dst, "null argument");
     HRB_CUDA(cudaSetDevice(h->device));
+    if (joinFlow(h)) return HRB_ERR_CUDA;
     const size_t flowBytes = 2 * (size_t)h->flowWidth * h->flowHeight * sizeof(int16_t);
     if (which == HRB_BUF_OFFSET_ARRAY) {
         HRB_REQUIRE(bytes == flowBytes, "size must be 2*flow_w*flow_h*2");
@@ -866,6 +910,7 @@ int hrb_ofc_write_flow(hrb_ofc* h, int which, const int16_t* src, size_t count) 
     HRB_REQUIRE(which == HRB_BUF_FLOW_FOR_WARP || which == HRB_BUF_FLOW_LATEST, "only the blurred flows are writable");
     HRB_REQUIRE(count == 2 * (size_t)h->flowWidth * h->flowHeight, "count must be 2*flow_w*flow_h");
     HRB_CUDA(cudaSetDevice(h->device));
+    if (joinFlow(h)) return HRB_ERR_CUDA;
     const int slot = which == HRB_BUF_FLOW_FOR_WARP ? 0 : 1;
     HRB_CUDA(cudaMemcpyAsync(h->blurredOffsetArray[slot], src, count * sizeof(int16_t), cudaMemcpyHostToDevice, h->stream));
     uint32_t peak = 0;
@@ -882,6 +927,7 @@ int hrb_ofc_write_flow(hrb_ofc* h, int which, const int16_t* src, size_t count) 
 int hrb_ofc_set_profile(hrb_ofc* h, int on) {
     HRB_REQUIRE(h, "null handle");
     HRB_CUDA(cudaSetDevice(h->device));
+    if (joinFlow(h)) return HRB_ERR_CUDA;
     const int rc = profResolve(h);
     if (rc) return rc;
     h->prof.on = on != 0;
@@ -924,6 +970,19 @@ int hrb_ofc_set_output_stripe(hrb_ofc* h, int row_begin, int row_end) {
     h->stripeY0 = row_begin;
     h->stripeY1 = row_end;
     return HRB_OK;
+}
+
+int hrb_ofc_set_flow_overlap(hrb_ofc* h, int on) {
+    HRB_REQUIRE(h, "null handle");
+    const int rc = joinFlow(h);
+    if (rc) return rc;
+    h->flowOverlap = on != 0;
+    return HRB_OK;
+}
+
+int hrb_ofc_join_flow(hrb_ofc* h) {
+    HRB_REQUIRE(h, "null handle");
+    return joinFlow(h);
 }
 
 int hrb_ofc_set_search_variant(hrb_ofc* h, int variant) {

@@ -130,6 +130,9 @@ struct hrb_ofc {
     // transfers run on their own streams so that the upload of frame N+1 and the downloads of the outputs of frame N
     // overlap the kernels: input slot [3] is the upload target (rotated in by updateFrame), the output is a ring of 3
     cudaStream_t upStream, downStream;
+    cudaStream_t flowStream;             // asynchronous flow calculations run here, beside the warps of the same source frame
+    cudaEvent_t flowForkEvent, flowJoinEvent;
+    bool flowJoinPending, flowOverlap;
     cudaEvent_t spareFreeEvent;          // compute stream: last readers of the buffer that became input slot [3] are enqueued
     static constexpr int kOutRing = 3;
     cudaEvent_t outReady[kOutRing];      // compute stream: warp/copy into ring slot i finished

@@ -277,6 +277,14 @@ class OpticalFlowCalc:
     def setSearchVariant(self, variant):
         self._check(self._lib.hrb_ofc_set_search_variant(self._h, int(variant)))
 
+    def setFlowOverlap(self, on):
+        """calculateOpticalFlowAsync on its own stream beside the following warps (default) or on the compute stream."""
+        self._check(self._lib.hrb_ofc_set_flow_overlap(self._h, 1 if on else 0))
+
+    def joinFlow(self):
+        """Order the compute stream behind the flow calculation still in flight (no host wait)."""
+        self._check(self._lib.hrb_ofc_join_flow(self._h))
+
     def setProfile(self, on):
         self._check(self._lib.hrb_ofc_set_profile(self._h, 1 if on else 0))
 

@@ -196,6 +196,12 @@ HRB_API int hrb_ofc_profile_reset(hrb_ofc* h);
  * double-buffered sliding kernel.
  * Results are identical; exists for A/B measurements and parity tests. */
 HRB_API int hrb_ofc_set_search_variant(hrb_ofc* h, int variant);
+/* hrb_ofc_calculate_optical_flow_async runs the search on its own stream, beside the warps issued after it (they read
+ * the PREVIOUS flow, opticalFlowCalcSDR.cpp:113-123,150).  on = 0 keeps everything on the compute stream.  Default 1. */
+HRB_API int hrb_ofc_set_flow_overlap(hrb_ofc* h, int on);
+/* Orders the compute stream (hrb_ofc_stream) behind the flow calculation still running on the flow stream, without
+ * blocking the host: work a caller enqueues on the compute stream afterwards sees the finished flow. */
+HRB_API int hrb_ofc_join_flow(hrb_ofc* h);
 /* number of kernels this library has launched in this process */
 HRB_API uint64_t hrb_kernel_launch_count(void);
 /* packed byte-SAD instruction peak of the device (VABSDIFF4.U8.ACC issue rate), in 1e9 byte-abs-diffs/s */

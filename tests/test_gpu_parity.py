@@ -437,3 +437,43 @@ def test_output_stripes_tile_the_full_frame(synth, hdr, mode):
         assert np.array_equal(merged, outs[0]), f"{op}: stripes do not tile the full frame"
         # a stripe download must leave the rest of the caller's buffer alone
         assert not outs[2][W * (H // n):W * H].any()
+
+
+@pytest.mark.parametrize("hdr,W,H", [(True, 3840, 2160), (False, 1920, 1080)])
+def test_overlapped_flow_equals_the_serial_schedule(synth, hdr, W, H):
+    """calculateOpticalFlowAsync runs the search on its own stream beside the warps of the same source frame.  At sizes
+    where the kernels really overlap, every output frame, every flow field and every frame delta must equal those of the
+    same calls with the overlap switched off (whose small-size equality with the oracle the other tests establish)."""
+    import torch
+    import hopperrender_b200 as hr
+    cls = hr.OpticalFlowCalcHDR if hdr else hr.OpticalFlowCalcSDR
+    dt = torch.int16 if hdr else torch.uint8
+    fs = [torch.from_numpy(f.view(np.int16) if hdr else f).cuda() for f in frames(synth, W, H, hdr, 6)]
+    results = []
+    for overlap in (True, False):
+        g = cls(H, W, 0, 0, 8, 6, 16.0, 235.0, 2160)
+        g.setFlowOverlap(overlap)
+        n_el = g.outputFrameBytes // (2 if hdr else 1)
+        outs, deltas, flows = [], [], []
+        pool = [torch.zeros(n_el, dtype=dt).pin_memory() for _ in range(12)]
+        tickets = []
+        for t, fr in enumerate(fs):
+            g.updateFrameDevice(fr)
+            if t >= 2:
+                g.calculateOpticalFlowAsync()
+                for j in range(3):
+                    g.warpFrames((0.3 * (3 * t + j)) % 1.0, 2)
+                    tickets.append(g.downloadFrameAsync(pool[len(tickets)]))
+        for tk in tickets:
+            g.waitDownload(tk)
+        g.synchronize()
+        outs = [p.numpy().copy() for p in pool[:len(tickets)]]
+        flows = g.readFlow(latest=True).copy()
+        results.append((outs, flows, g.m_totalFrameDelta))
+        g.close()
+    (oa, fa, da), (ob, fb, db) = results
+    assert len(oa) == len(ob) == 12
+    for i, (x, y) in enumerate(zip(oa, ob)):
+        assert np.array_equal(x, y), f"output frame {i} differs between the overlapped and the serial schedule"
+    assert np.array_equal(fa, fb) and da == db
+    assert np.abs(fa).max() > 0
