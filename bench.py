@@ -52,6 +52,16 @@ def peaks():
     return {"hbm_gbs": 6650.0}, "fallback"
 
 
+def ncu_traffic(workload, kernel):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` capture of this
+    workload (profiles/ncu_traffic.json, written by tools/ncu_summary.py), or None."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as f:
+            return json.load(f)[workload][kernel]["dram_bytes_per_launch"]
+    except Exception:  # noqa: BLE001
+        return None
+
+
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)."""
     Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
@@ -301,6 +311,136 @@ def run_split(args, wl):
         dist.destroy_process_group()
 
 
+
+# ------------------------------------------------------------------------------------------------------
+# several independent streams per GPU: S handles per device, one host thread round-robin
+# ------------------------------------------------------------------------------------------------------
+def run_streams(args, wl):
+    import torch
+    import torch.distributed as dist
+
+    import hopperrender_b200 as hr
+    from hopperrender_b200 import replay, shard, synth
+
+    rank, world, local = dist_env()
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device — hopperrender_b200 has no CPU fallback")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    S = args.streams_per_gpu
+    W, H, hdr = wl["W"], wl["H"], wl["hdr"]
+    cls = hr.OpticalFlowCalcHDR if hdr else hr.OpticalFlowCalcSDR
+    tstreams = [torch.cuda.Stream() for _ in range(S)]
+    calcs = [cls(H, W, 0, 0, 8, 6, 0.0, 255.0, wl["maxres"], device=local, stream=ts.cuda_stream) for ts in tstreams]
+    for c in calcs:
+        c.m_opticalFlowSearchRadius = args.radius
+        if args.no_overlap:
+            c.setFlowOverlap(False)
+    RING = 6
+    tdt = torch.int16 if hdr else torch.uint8
+    host_frames = [synth.make_frame(W, H, t, synth.SEED_BASE + 2 + rank, hdr) for t in range(RING)]
+    pinned = [torch.from_numpy(f.view(np.int16) if hdr else f).pin_memory() for f in host_frames]
+    dev = [p.cuda() for p in pinned]
+    torch.cuda.synchronize()
+    sched = replay.output_schedule(5 * (args.warmup + args.steps) + 128, wl["target"], replay.SOURCE_FRAME_TIME_23976)
+    POOL = 8
+    n_el = calcs[0].outputFrameBytes // (2 if hdr else 1)
+    pools = [[torch.empty(n_el, dtype=tdt).pin_memory() for _ in range(POOL)] for _ in range(S)]
+    pending = [[] for _ in range(S)]
+    counts = [0] * S
+
+    def step_device(h, i):
+        c = calcs[h]
+        c.updateFrameDevice(dev[(i + h) % RING])
+        c.calculateOpticalFlowAsync()
+        for b in sched[i]:
+            c.warpFrames(b, hr.BlendedFrame)
+        return len(sched[i])
+
+    def step_e2e(h, i):
+        c = calcs[h]
+        c.updateFrame(pinned[(i + h) % RING])
+        c.calculateOpticalFlowAsync()
+        for b in sched[i]:
+            c.warpFrames(b, hr.BlendedFrame)
+            pending[h].append(c.downloadFrameAsync(pools[h][counts[h] % POOL]))
+            counts[h] += 1
+        while len(pending[h]) > POOL - 2:
+            c.waitDownload(pending[h].pop(0))
+        return len(sched[i])
+
+    def sync_all():
+        for h, c in enumerate(calcs):
+            while pending[h]:
+                c.waitDownload(pending[h].pop(0))
+            c.synchronize()
+        torch.cuda.synchronize()
+        shard.barrier()
+
+    idx = 0
+    for i in range(3):
+        for h in range(S):
+            calcs[h].updateFrameDevice(dev[(i + h) % RING])
+    for _ in range(args.warmup):
+        for h in range(S):
+            step_device(h, idx)
+        idx += 1
+    sync_all()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    launches0 = hr.kernel_launch_count()
+    e0 = torch.cuda.Event(enable_timing=True)
+    ends = [torch.cuda.Event(enable_timing=True) for _ in range(S)]
+    e0.record(torch.cuda.current_stream())   # the device is idle here: every stream's work starts after this point
+    frames = 0
+    for _ in range(args.steps):
+        for h in range(S):
+            frames += step_device(h, idx)
+        idx += 1
+    for h in range(S):
+        calcs[h].joinFlow()
+        ends[h].record(tstreams[h])
+    sync_all()
+    ms = shard.combine(0, max(e0.elapsed_time(e) for e in ends))[1]
+    launches = shard.combine(hr.kernel_launch_count() - launches0, 0.0)[0]
+    clocks = sampler.stop() if rank == 0 else None
+    total_frames = shard.combine(frames, 0.0)[0]
+    value = total_frames / (ms * 1e-3)
+
+    esteps = min(args.steps, 50)
+    for _ in range(2):
+        for h in range(S):
+            step_e2e(h, idx)
+        idx += 1
+    sync_all()
+    t0 = time.perf_counter()
+    eframes = 0
+    for _ in range(esteps):
+        for h in range(S):
+            eframes += step_e2e(h, idx)
+        idx += 1
+    sync_all()
+    wall_ms = shard.combine(0, (time.perf_counter() - t0) * 1e3)[1]
+    e2e_value = shard.combine(eframes, 0.0)[0] / (wall_ms * 1e-3)
+    if rank == 0:
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+                "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8",
+                "data": "synthetic",
+                "config": {"workload": f"{args.workload}: {wl['desc']}, R={args.radius}", "search_radius": args.radius,
+                           "streams_per_gpu": S, "flow_overlap": not args.no_overlap,
+                           "note": "a step = one source frame of EVERY stream; S independent handles per GPU driven round-robin by one host thread",
+                           "l2": "each stream's per-step working set (~265 MB at cfg3) exceeds the 126 MB L2"},
+                "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(S * calcs[0].inputFrameBytes),
+                        "d2h_bytes_per_step": int(round(eframes / esteps * calcs[0].outputFrameBytes)), "steps": esteps},
+                "gpu_launches": int(launches), "clocks": clocks}
+        print(json.dumps(line), flush=True)
+    for c in calcs:
+        c.close()
+    if world > 1:
+        dist.destroy_process_group()
+
 # ------------------------------------------------------------------------------------------------------
 # the CUDA arm
 # ------------------------------------------------------------------------------------------------------
@@ -314,6 +454,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-overlap", action="store_true", help="keep the asynchronous flow calculation on the compute stream (A/B)")
     ap.add_argument("--radius", type=int, default=SEARCH_RADIUS)
+    ap.add_argument("--streams-per-gpu", type=int, default=1, help="independent video streams (handles) per GPU; >1 prints the multi-stream line")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     wl = WORKLOADS[args.workload]
@@ -322,6 +463,9 @@ def main():
         return
     if args.workload == "cfg4":
         run_split(args, wl)
+        return
+    if args.streams_per_gpu > 1:
+        run_streams(args, wl)
         return
 
     import torch
@@ -445,6 +589,33 @@ def main():
     total_frames = sum_over_ranks(frames)
     value = total_frames / (ms * 1e-3)
 
+    # ---- the same loop at the auto-tuner's lower bound R=5 ("also report R = 5") ----
+    r5 = None
+    if args.radius != 5:
+        calc.m_opticalFlowSearchRadius = 5
+        for _ in range(3):
+            step_device(idx)
+            idx += 1
+        calc.synchronize()
+        r0, r1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        r5_steps = min(args.steps, 100)
+        r5_frames = 0
+        with torch.cuda.stream(stream):
+            r0.record(stream)
+            for _ in range(r5_steps):
+                r5_frames += step_device(idx)
+                idx += 1
+            calc.joinFlow()
+            r1.record(stream)
+        calc.synchronize()
+        r5_ms = max_over_ranks(r0.elapsed_time(r1))
+        r5 = {"value": sum_over_ranks(r5_frames) / (r5_ms * 1e-3), "unit": UNIT, "ms_per_step": r5_ms / r5_steps, "steps": r5_steps}
+        calc.m_opticalFlowSearchRadius = args.radius
+        for _ in range(2):
+            step_device(idx)
+            idx += 1
+        calc.synchronize()
+
     # ---- per-kernel breakdown (same loop, CUDA events around every kernel class on the handle's stream) ----
     calc.setProfile(True)
     calc.profileReset()
@@ -510,15 +681,17 @@ def main():
                     "blocking_api_value": e2e_blocking_value},
             "gpu_launches": int(launches),
             "clocks": clocks,
-            "roofline": {"kernel": "warpFrameKernel (dominant HBM-bound kernel, %d launches/step)" % round(mean_out), "bound": "hbm",
-                         "achieved": warp_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": warp_gbs / hbm_peak, "traffic": None,
+            "roofline": {"kernel": "warpFastKernel = warpFrames (dominant HBM-bound kernel, %d launches/step)" % round(mean_out), "bound": "hbm",
+                         "achieved": warp_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": warp_gbs / hbm_peak,
+                         "traffic": ncu_traffic(args.workload, "warpFastKernel"),
                          "peak_source": f"{pk_kind} (MEASURED_PEAKS.json hbm_gbs)", "algorithmic_bytes_per_launch": alg["warp"],
                          "avg_launch_ms": warp_ms},
-            "roofline_search": {"kernel": "sadPassKernel ladder (dominant by time, integer-ALU bound)", "bound": "int_alu",
+            "roofline_search": {"kernel": "search ladder: sadSlideStagedKernel + sadCandKernel, %d passes (dominant by time, integer-ALU bound)" % alg["passes"], "bound": "int_alu",
                                 "achieved": absdiff_rate, "peak": sad_peak, "unit": "G byte-absdiff/s",
                                 "frac": (absdiff_rate / sad_peak) if sad_peak else None,
                                 "peak_source": "hrb_microbench_sad_peak: VABSDIFF4.U8.ACC issue rate measured in this run",
                                 "algorithmic_absdiff_per_step": 3 * args.radius * alg["L"] * alg["passes"], "ms_per_step": search_ms_per_step},
+            "search_radius_5": r5,
             "breakdown_ms_per_step": {"ingest": prof["ms_ingest"] / psteps, "search": search_ms_per_step, "blur": prof["ms_blur"] / psteps,
                                       "warp": prof["ms_warp"] / psteps, "kernels_total": step_kernel_ms},
         }

@@ -73,17 +73,80 @@ def raw(tag, which, out, picks=None):
     out.write("\n")
 
 
+def step(tag, out, workload):
+    """Every kernel of one steady-state step from the `--set full` capture; also writes profiles/ncu_traffic.json."""
+    import json
+    path = os.path.join(ROOT, "gpurun_out", "prof", f"step_raw_{tag}.csv")
+    if not os.path.exists(path):
+        return
+    rows = list(csv.reader(open(path)))
+    hdr, units, data = rows[0], rows[1], rows[2:]
+    idx = {h: i for i, h in enumerate(hdr)}
+    names = [short(d[idx["Kernel Name"]]) for d in data]
+    # one step = from a packFrameKernel to the next
+    packs = [i for i, n in enumerate(names) if "packFrame" in n]
+    a, b = (packs[0], packs[1]) if len(packs) > 1 else (0, len(data))
+    sel = list(range(a, b))
+
+    def val(i, k):
+        try:
+            return float(data[i][idx[k]].replace(",", ""))
+        except Exception:  # noqa: BLE001
+            return float("nan")
+
+    def mb(i, k):  # ncu prints bytes with a per-column unit
+        u = units[idx[k]].lower()
+        scale = {"byte": 1e-6, "kbyte": 1e-3, "mbyte": 1.0, "gbyte": 1e3}.get(u, 1.0)
+        return val(i, k) * scale
+
+    out.write(f"## `ncu --set full --clock-control none` — every kernel of one steady-state step ({len(sel)} launches)\n\n")
+    cols = [("us", "gpu__time_duration.sum"), ("regs", "launch__registers_per_thread"), ("grid", "launch__grid_size"),
+            ("warps act %", "sm__warps_active.avg.pct_of_peak_sustained_active"), ("issue act %", "smsp__issue_active.avg.pct_of_peak_sustained_active"),
+            ("ALU pipe %", "sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active"),
+            ("DRAM %", "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed"), ("L2 hit %", "lts__t_sector_hit_rate.pct"),
+            ("warp-instr M", "smsp__inst_executed.sum"),
+            ("stall long_sb", "smsp__average_warps_issue_stalled_long_scoreboard_per_issue_active.ratio"),
+            ("stall math", "smsp__average_warps_issue_stalled_math_pipe_throttle_per_issue_active.ratio"),
+            ("stall barrier", "smsp__average_warps_issue_stalled_barrier_per_issue_active.ratio")]
+    out.write("| # | kernel | " + " | ".join(c for c, _ in cols) + " | DRAM rd MB | DRAM wr MB |\n|---|---|" + "---|" * (len(cols) + 2) + "\n")
+    traffic = collections.OrderedDict()
+    tot_us = 0.0
+    for i in sel:
+        cells = []
+        for c, k in cols:
+            v = val(i, k)
+            if c == "warp-instr M":
+                v /= 1e6
+            cells.append(f"{v:.1f}" if c not in ("regs", "grid") else f"{v:.0f}")
+        rd, wr = mb(i, "dram__bytes_read.sum"), mb(i, "dram__bytes_write.sum")
+        tot_us += val(i, "gpu__time_duration.sum")
+        out.write(f"| {i - a} | `{names[i][:48]}` | " + " | ".join(cells) + f" | {rd:.1f} | {wr:.1f} |\n")
+        key = names[i].split("<")[0]
+        t = traffic.setdefault(key, [0, 0.0])
+        t[0] += 1
+        t[1] += (rd + wr) * 1e6
+    out.write(f"\nSum of the step's kernel durations under ncu (cold caches, serialised): {tot_us:.0f} us.\n\n")
+    tj = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    try:
+        allw = json.load(open(tj))
+    except Exception:  # noqa: BLE001
+        allw = {}
+    allw[workload] = {k: {"launches": v[0], "dram_bytes_per_launch": int(v[1] / v[0]), "source": f"profiles/ncu_summary_{tag}.md"} for k, v in traffic.items()}
+    json.dump(allw, open(tj, "w"), indent=1)
+    out.write("Per-kernel DRAM traffic (dram__bytes_read.sum + dram__bytes_write.sum, mean per launch) is also written to `profiles/ncu_traffic.json`, "
+              "which `bench.py` reports as `roofline.traffic`.\n\n")
+
+
 def main():
     tag = sys.argv[1]
-    picks = [int(x) for x in sys.argv[2].split(",")] if len(sys.argv) > 2 else None
+    workload = sys.argv[2] if len(sys.argv) > 2 else "cfg3"
     os.makedirs(os.path.join(ROOT, "profiles"), exist_ok=True)
     dst = os.path.join(ROOT, "profiles", f"ncu_summary_{tag}.md")
     with open(dst, "w") as out:
-        out.write(f"# ncu summary {tag}\n\nCommand: `python bench.py --steps 2 --warmup 3 --no-cpu-baseline` under ncu (tools/gpu_profile.sh); "
-                  "numbers taken under the profiler are for SHARES and per-kernel counters only, never bench values.\n\n")
+        out.write(f"# ncu summary {tag} ({workload})\n\nCommand: `python bench.py --workload {workload} --steps 2 --warmup 3 --no-cpu-baseline` under ncu "
+                  "(tools/gpu_profile.sh); numbers taken under the profiler are for SHARES and per-kernel counters only, never bench values.\n\n")
         launches(tag, out)
-        raw(tag, "warp", out, [0])
-        raw(tag, "sad", out, picks)
+        step(tag, out, workload)
     print("wrote", dst)
 
 
