@@ -130,7 +130,7 @@ template <int R, int STEP, int NWARPS> __global__ void __launch_bounds__(32 * NW
 // pipe, and rows shared by the stacked runs cross L2 -> SM once.
 constexpr int SSP = 36;  // staged row pitch in words: 32 + alignment slack, 9 x 16 B
 
-template <int R, int STEP, int NW, int WU> __global__ void __launch_bounds__(32 * NW * WU) sadSlideStagedKernel(const SearchArgs a) {
+template <int R, int STEP, int NW, int WU> __global__ void __launch_bounds__(32 * NW * WU, 768 / (32 * NW * WU)) sadSlideStagedKernel(const SearchArgs a) {
     // tile = 32*WU columns x 32*NW rows inside ONE window; warp (wu, wv) owns the 32 x 32 sub-tile at (32*wu, 32*wv).
     // Wider tiles (WU = 2) make the staged row segments 272 B long: fewer, longer DRAM bursts per row.
     constexpr int LO = CandSpan<R>::LO, SPAN = CandSpan<R>::SPAN;

@@ -20,11 +20,13 @@ namespace {
 
 constexpr int CT_U = 32, CT_V = 128;  // tile
 constexpr int SP = 52;                 // staged row pitch in words (48 + alignment slack, 13 x 16 B)
-constexpr int RV_MAX = 256;            // staged rows: 128 + (HI-LO <= 113) + spread_v (<= 15)
+constexpr int RV_MAX = 254;            // staged rows: 128 + (HI-LO <= 113) + spread_v (<= 13); sized so that four CTAs fit an SM
 constexpr int RU_MAX = 48;             // staged columns actually addressed
-constexpr int MAX_WIN = (CT_U / 2) * (CT_V / 2);  // windows of a tile at ws = 2
-constexpr int MAX_SUMWIN = (CT_U / 8) * (CT_V / 8);
-constexpr size_t CAND_SMEM = (size_t)RV_MAX * SP * 4 + MAX_SUMWIN * 16 * 4 + MAX_WIN * 4 + 16;
+// dynamic shared memory of one CTA: staged region + (ws >= 8) per-window sums + per-window offsets + 4 range words
+template <int WS> __host__ __device__ constexpr int candWindows() { return (CT_U / WS) * (CT_V / WS); }
+template <int WS> __host__ __device__ constexpr int candSumWords() { return WS >= 8 ? candWindows<WS>() * 16 : 0; }
+template <int WS> __host__ __device__ constexpr size_t candSmem() { return ((size_t)RV_MAX * SP + candSumWords<WS>() + candWindows<WS>() + 4) * 4; }
+static_assert(candSmem<2>() + 1024 <= 232448 / 4, "four CTAs per SM");
 
 // lean per-layer total for the in-register finalize: same arithmetic as windowTotal, candidate offset given
 __device__ __forceinline__ uint32_t layerTotal(const SearchArgs& a, const WindowCtx& c, uint32_t sad, int sq) {
@@ -169,15 +171,15 @@ __device__ __forceinline__ void candGroups(const SearchArgs& a, const View<STEP>
     }
 }
 
-template <int R, int STEP, bool TAPS, int WS> __global__ void __launch_bounds__(256) sadCandKernel(const SearchArgs a) {
+template <int R, int STEP, bool TAPS, int WS> __global__ void __launch_bounds__(256, 4) sadCandKernel(const SearchArgs a) {
     constexpr int LO = candOffset<R>(0), HI = candOffset<R>(R - 1), SPAN = HI - LO;
     constexpr int wsLog2 = WS == 2 ? 1 : WS == 4 ? 2 : WS == 8 ? 3 : WS == 16 ? 4 : 5;
     constexpr int nwu = CT_U >> wsLog2, nwv = CT_V >> wsLog2;  // windows of the tile along u, v
     extern __shared__ __align__(16) uint32_t smem[];
     uint32_t* __restrict__ s_f1 = smem;                                        // [RV_MAX][SP]
-    uint32_t (*s_sums)[16] = reinterpret_cast<uint32_t (*)[16]>(smem + RV_MAX * SP);  // [window inside the tile][layer] (ws 8, 16)
-    int* __restrict__ s_off = reinterpret_cast<int*>(smem + RV_MAX * SP + MAX_SUMWIN * 16);  // per window: (ou & 0xffff) | (ov << 16)
-    int* __restrict__ s_rng = s_off + MAX_WIN;                                 // min ou, max ou, min ov, max ov
+    uint32_t (*s_sums)[16] = reinterpret_cast<uint32_t (*)[16]>(smem + RV_MAX * SP);  // [window inside the tile][layer] (ws >= 8)
+    int* __restrict__ s_off = reinterpret_cast<int*>(smem + RV_MAX * SP + candSumWords<WS>());  // per window: (ou & 0xffff) | (ov << 16)
+    int* __restrict__ s_rng = s_off + candWindows<WS>();                       // min ou, max ou, min ov, max ov
 
     const View<STEP> vw(a);
     const int lane = threadIdx.x, warp = threadIdx.y;
@@ -265,12 +267,12 @@ template <int R, int STEP, bool TAPS, int WS> __global__ void __launch_bounds__(
 template <int R, int STEP, bool TAPS, int WS> int launchCandOne(hrb_ofc* h, const SearchArgs& a) {
     static bool configured = false;
     if (!configured) {
-        HRB_CUDA(cudaFuncSetAttribute(sadCandKernel<R, STEP, TAPS, WS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CAND_SMEM));
+        HRB_CUDA(cudaFuncSetAttribute(sadCandKernel<R, STEP, TAPS, WS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)candSmem<WS>()));
         configured = true;
     }
     const int lu = STEP == 1 ? a.lw : a.lh, lv = STEP == 1 ? a.lh : a.lw;
     const dim3 grid((lu + CT_U - 1) / CT_U, (lv + CT_V - 1) / CT_V, 1);
-    sadCandKernel<R, STEP, TAPS, WS><<<grid, dim3(32, 8, 1), CAND_SMEM, h->stream>>>(a);
+    sadCandKernel<R, STEP, TAPS, WS><<<grid, dim3(32, 8, 1), candSmem<WS>(), h->stream>>>(a);
     HRB_LAUNCH_CHECK();
     return HRB_OK;
 }
