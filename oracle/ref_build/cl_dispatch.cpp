@@ -5,6 +5,7 @@
 // the reference's buffers after every search pass without touching the reference's sources.
 #include <CL/cl.h>
 #include <dlfcn.h>
+#include <unistd.h>
 #include <stdio.h>
 #include <stdlib.h>
 
@@ -18,6 +19,9 @@ extern "C" const char* hrref_opencl_library() { return g_libName.c_str(); }
 static void* resolve(const char* name) {
     if (!g_lib) {
         const char* env = getenv("HRREF_OPENCL_LIB");
+        // a box with the NVIDIA driver but no /etc/OpenCL/vendors/*.icd: tell the ICD loader which vendor library to load
+        if (!getenv("OCL_ICD_FILENAMES") && !getenv("OCL_ICD_VENDORS") && access("/etc/OpenCL/vendors/nvidia.icd", R_OK) != 0)
+            setenv("OCL_ICD_FILENAMES", "libnvidia-opencl.so.1", 1);
         const char* candidates[] = {env, "libOpenCL.so.1", "libnvidia-opencl.so.1", "libOpenCL.so"};
         for (const char* c : candidates) {
             if (!c || !*c) continue;

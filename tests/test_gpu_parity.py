@@ -112,6 +112,11 @@ SEARCH_CASES = [
     (False, 722, 430, 430, 0, 16, "scene"),     # partial 32x32 tiles on both edges, windows 512..2
     (True, 640, 384, 384, 672, 7, "scene"),
     (False, 450, 258, 258, 0, 12, "random"),    # large offsets: mirrored halos in the sliding-window kernels
+    (False, 200, 120, 270, 0, 2, "scene"),      # radii below the filter's minimum of 5 take the generic kernel
+    (True, 200, 120, 270, 0, 3, "random"),
+    (False, 290, 170, 270, 0, 13, "scene"),
+    (True, 290, 170, 270, 300, 15, "random"),
+    (False, 272, 160, 270, 0, 4, "ramp"),
 ]
 
 

@@ -2,8 +2,7 @@
 # quick visit: search-ladder parity tests + launch list of a short bench + (optionally) a full capture of selected kernels
 set -u
 TAG=${1:-q}
-mkdir -p gpurun_out/prof /etc/OpenCL/vendors
-[ -f /etc/OpenCL/vendors/nvidia.icd ] || echo libnvidia-opencl.so.1 > /etc/OpenCL/vendors/nvidia.icd
+mkdir -p gpurun_out/prof
 timeout 900 python -m pytest tests/test_gpu_parity.py -m gpu -q -x -k "search or smoke or filter or device_resident or warp or levels or pipelined or cpp_shim or overlapped" > gpurun_out/pytest_quick.log 2>&1; echo "pytest rc=$?" >> gpurun_out/pytest_quick.log
 tail -5 gpurun_out/pytest_quick.log
 BENCH="python bench.py --steps 2 --warmup 3 --no-cpu-baseline"

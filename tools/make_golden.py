@@ -4,8 +4,7 @@ classes and OpenCL kernel strings) on an OpenCL device.  Run on the GPU box, whe
 implementation executes the reference's kernels on the B200 (32-wide lock-step warps = the semantics the
 reference's barrier-free reduction relies on):
 
-    gpurun -- 'mkdir -p /etc/OpenCL/vendors && echo libnvidia-opencl.so.1 > /etc/OpenCL/vendors/nvidia.icd; \
-               python tools/make_golden.py gpurun_out/golden'
+    gpurun -- 'python tools/make_golden.py gpurun_out/golden'
 
 Each file holds the input frames and, per search pass, the window sums / winning layers at the window
 representatives and the offset array, then the blurred flow, m_totalFrameDelta and output frames.
