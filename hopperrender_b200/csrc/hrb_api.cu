@@ -134,31 +134,10 @@ static int resolveFlow(hrb_ofc* h) {
     return HRB_OK;
 }
 
-static int enqueueFlow(hrb_ofc* h) {
-    HRB_CUDA(cudaSetDevice(h->device));
-    hrb_ofc::FlowRecord& rec = h->flowRec[h->curRec];
-    if (rec.pending) {  // a second calculate on the same upload: its end event is about to be re-recorded
-        const int rc = resolveFlow(h);
-        if (rc) return rc;
-    }
-    const int R = h->searchRadius;  // m_lowGrid8x8xL[2] = m_opticalFlowSearchRadius, opticalFlowCalcSDR.cpp:46
-    if (R < 2 || R > 16) {
-        setLastError("[hopperrender_b200] search radius %d outside 2..16", R);
-        return HRB_ERR_INVALID_ARG;
-    }
-    if (h->deltaScalar < 0 || h->deltaScalar > 31 || h->neighborBiasScalar < 0 || h->neighborBiasScalar > 31) {
-        setLastError("[hopperrender_b200] delta/neighbor scalar outside 0..31");
-        return HRB_ERR_INVALID_ARG;
-    }
+// The search ladder and the blur of one flow calculation.  issue = false only replays the host-side bookkeeping
+// (the kernels are then launched from a captured graph).
+static int issueFlowKernels(hrb_ofc* h, int R, int ws0, int iterations, bool issue) {
     const int lw = h->flowWidth, lh = h->flowHeight;
-    int ws0, iterations;
-    ladder(lw, lh, &ws0, &iterations);
-    if (!rec.startValid) {  // calculate without a preceding updateFrame: time from here
-        HRB_CUDA(cudaEventRecord(rec.start, h->stream));
-        rec.startValid = true;
-    }
-    if (h->tapMode) freeTaps(h);
-
     SearchArgs a;
     memset(&a, 0, sizeof(a));
     a.plane1 = h->searchPlane[1];  // frame1 = m_inputFrameArray[1], opticalFlowCalcSDR.cpp:79
@@ -215,8 +194,10 @@ static int enqueueFlow(hrb_ofc* h) {
                 a.tapLayer = t.layer;
                 h->taps.push_back(t);
             }
-            const int rc = launchSearchPass(h, a, R, step);
-            if (rc) return rc;
+            if (issue) {
+                const int rc = launchSearchPass(h, a, R, step);
+                if (rc) return rc;
+            }
             if (h->tapMode) {
                 PassTapDev& t = h->taps.back();
                 const size_t nW = (size_t)a.nWx * a.nWy;
@@ -249,9 +230,98 @@ static int enqueueFlow(hrb_ofc* h) {
     h->haveFlowLevels = true;
 
     // blur into m_blurredOffsetArray[0], then swap (opticalFlowCalcSDR.cpp:113-123)
-    {
+    if (issue) {
         const int rc = launchBlurFlow(h, h->levelOffsets[h->lastIterParity][0], h->levelOffsets[h->lastIterParity][1], h->lastNWx, ilog2(h->lastWs),
                                       h->blurredOffsetArray[0], h->flowMaxDev[0]);
+        if (rc) return rc;
+    }
+    return HRB_OK;
+}
+
+static void dropFlowGraphs(hrb_ofc* h) {
+    for (auto& g : h->flowGraphs)
+        if (g.exec) cudaGraphExecDestroy(g.exec);
+    h->flowGraphs.clear();
+}
+
+// Launches the flow kernels through a CUDA graph captured on first use for this combination of buffers and parameters
+// (24 dependent launches at 4K become one); falls back to plain launches whenever capture is not possible.
+static int launchFlowKernels(hrb_ofc* h, int R, int ws0, int iterations) {
+    if (!h->flowGraphsOn || h->tapMode || h->prof.on) return issueFlowKernels(h, R, ws0, iterations, true);
+    hrb_ofc::FlowGraph key;
+    key.plane1 = h->searchPlane[1];
+    key.plane2 = h->searchPlane[2];
+    key.blurOut = h->blurredOffsetArray[0];
+    key.R = R;
+    key.deltaScalar = h->deltaScalar;
+    key.neighborBiasScalar = h->neighborBiasScalar;
+    key.variant = h->searchVariant;
+    hrb_ofc::FlowGraph* hit = nullptr;
+    for (auto& g : h->flowGraphs)
+        if (g.plane1 == key.plane1 && g.plane2 == key.plane2 && g.blurOut == key.blurOut && g.R == key.R && g.deltaScalar == key.deltaScalar &&
+            g.neighborBiasScalar == key.neighborBiasScalar && g.variant == key.variant)
+            hit = &g;
+    if (!hit) {
+        if (h->flowGraphs.size() >= 32) dropFlowGraphs(h);  // parameters keep changing (auto-tuner, UI): start over
+        const unsigned long long before = g_launchCount;
+        if (cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal) != cudaSuccess) {
+            cudaGetLastError();
+            h->flowGraphsOn = false;  // e.g. the caller's stream is the legacy default stream
+            return issueFlowKernels(h, R, ws0, iterations, true);
+        }
+        const int rc = issueFlowKernels(h, R, ws0, iterations, true);
+        cudaGraph_t graph = nullptr;
+        const cudaError_t ce = cudaStreamEndCapture(h->stream, &graph);
+        key.launches = (unsigned)(g_launchCount - before);
+        g_launchCount = before;  // nothing has run yet
+        key.exec = nullptr;
+        if (rc == HRB_OK && ce == cudaSuccess && graph && cudaGraphInstantiate(&key.exec, graph, 0) == cudaSuccess) {
+            cudaGraphDestroy(graph);
+            h->flowGraphs.push_back(key);
+            hit = &h->flowGraphs.back();
+        } else {
+            if (graph) cudaGraphDestroy(graph);
+            cudaGetLastError();
+            h->flowGraphsOn = false;
+            if (rc) return rc;
+            return issueFlowKernels(h, R, ws0, iterations, true);
+        }
+    } else {
+        const int rc = issueFlowKernels(h, R, ws0, iterations, false);
+        if (rc) return rc;
+    }
+    HRB_CUDA(cudaGraphLaunch(hit->exec, h->stream));
+    g_launchCount += hit->launches;
+    return HRB_OK;
+}
+
+static int enqueueFlow(hrb_ofc* h) {
+    HRB_CUDA(cudaSetDevice(h->device));
+    hrb_ofc::FlowRecord& rec = h->flowRec[h->curRec];
+    if (rec.pending) {  // a second calculate on the same upload: its end event is about to be re-recorded
+        const int rc = resolveFlow(h);
+        if (rc) return rc;
+    }
+    const int R = h->searchRadius;  // m_lowGrid8x8xL[2] = m_opticalFlowSearchRadius, opticalFlowCalcSDR.cpp:46
+    if (R < 2 || R > 16) {
+        setLastError("[hopperrender_b200] search radius %d outside 2..16", R);
+        return HRB_ERR_INVALID_ARG;
+    }
+    if (h->deltaScalar < 0 || h->deltaScalar > 31 || h->neighborBiasScalar < 0 || h->neighborBiasScalar > 31) {
+        setLastError("[hopperrender_b200] delta/neighbor scalar outside 0..31");
+        return HRB_ERR_INVALID_ARG;
+    }
+    const int lw = h->flowWidth, lh = h->flowHeight;
+    int ws0, iterations;
+    ladder(lw, lh, &ws0, &iterations);
+    if (!rec.startValid) {  // calculate without a preceding updateFrame: time from here
+        HRB_CUDA(cudaEventRecord(rec.start, h->stream));
+        rec.startValid = true;
+    }
+    if (h->tapMode) freeTaps(h);
+
+    {
+        const int rc = launchFlowKernels(h, R, ws0, iterations);
         if (rc) return rc;
     }
     HRB_CUDA(cudaMemcpyAsync(rec.rawDeltaHost, h->rawDeltaDev, sizeof(uint32_t), cudaMemcpyDeviceToHost, h->stream));
@@ -410,6 +480,7 @@ int hrb_ofc_create(hrb_ofc** out, const hrb_ofc_desc* d) {
     }
     h->haveFlowLevels = false;
     h->tapMode = false;
+    h->flowGraphsOn = true;
     h->searchVariant = 0;
     h->warpVariant = 0;
     h->smCount = 148;
@@ -578,6 +649,7 @@ void hrb_ofc_destroy(hrb_ofc* h) {
     for (auto e : h->ticketEvent)
         if (e) cudaEventDestroy(e);
     if (h->spareFreeEvent) cudaEventDestroy(h->spareFreeEvent);
+    dropFlowGraphs(h);
     if (h->upStream) cudaStreamDestroy(h->upStream);
     if (h->flowStream) cudaStreamDestroy(h->flowStream);
     if (h->flowForkEvent) cudaEventDestroy(h->flowForkEvent);

@@ -169,6 +169,18 @@ struct hrb_ofc {
     int warpVariant;    // 0: automatic (table-driven fast kernel for modes 0-2), 1: generic warpFrameKernel for every mode
     int smCount;
     bool tapMode;
+    // instantiated CUDA graphs of the flow calculation (search ladder + blur), one per combination of buffers and
+    // parameters it was captured with: the input slots rotate with period 4, so a handful of graphs serve a stream
+    struct FlowGraph {
+        const void* plane1;
+        const void* plane2;
+        const void* blurOut;
+        int R, deltaScalar, neighborBiasScalar, variant;
+        cudaGraphExec_t exec;
+        unsigned launches;
+    };
+    std::vector<FlowGraph> flowGraphs;
+    bool flowGraphsOn;
     std::vector<hrb::PassTapDev> taps;
     hrb::Profile prof;
 };
