@@ -9,7 +9,7 @@
 //     offset / neighbour bias of a window is (pixel count) x (a per-window constant);
 //   * sums are uint32 modulo 2^32, so any summation order is bit-exact.
 // Nothing is zero-filled or materialised per flow pixel: windows that fit a CTA tile are reduced and
-// arg-min'ed inside the SAD kernel; larger windows go through R atomics per tile and a tiny finalize.
+// arg-min'ed inside the SAD kernel; larger windows go through R atomics per tile, the last tile of a window finalizes it.
 #include "search_common.cuh"
 
 namespace hrb {
@@ -132,28 +132,43 @@ template <int R, int STEP> __global__ void __launch_bounds__(256) sadPassKernel(
                 const int wx = View<STEP>::wx(wu, wv), wy = View<STEP>::wy(wu, wv);
                 if (wx < a.nWx && wy < a.nWy) finalizeWindow<R, STEP>(a, wx, wy, s_sums[tid]);
             }
-        } else if (tid < R) {
+        } else {
+            // the tile lies inside one window larger than the tile: add to the window's global sums; the CTA that
+            // arrives last (ticket) finds them complete, does the arg-min and leaves sums and ticket zeroed for the next pass
+            __shared__ bool s_last;
             const int wu = (blockIdx.x * TILE) >> a.wsLog2, wv = (blockIdx.y * TILE) >> a.wsLog2;
-            atomicAdd(&a.winSums[(size_t)(View<STEP>::wy(wu, wv) * a.nWx + View<STEP>::wx(wu, wv)) * 16 + tid], s_sums[0][tid]);
+            const int wx = View<STEP>::wx(wu, wv), wy = View<STEP>::wy(wu, wv);
+            const size_t w = (size_t)(wy * a.nWx + wx);
+            if (tid < R) {
+                atomicAdd(&a.winSums[w * 16 + tid], s_sums[0][tid]);
+                __threadfence();
+            }
+            __syncthreads();
+            if (tid == 0) {
+                const int x0 = wx << a.wsLog2, y0 = wy << a.wsLog2;
+                const unsigned tiles = (unsigned)(((min(ws, a.lw - x0) + TILE - 1) / TILE) * ((min(ws, a.lh - y0) + TILE - 1) / TILE));
+                s_last = atomicAdd(&a.winTicket[w], 1u) == tiles - 1;
+            }
+            __syncthreads();
+            if (s_last && tid == 0) {
+                __threadfence();
+                uint32_t sums[16];
+#pragma unroll
+                for (int z = 0; z < 16; ++z) {
+                    sums[z] = z < R ? __ldcg(&a.winSums[w * 16 + z]) : 0u;
+                    if (z < R) a.winSums[w * 16 + z] = 0;
+                }
+                a.winTicket[w] = 0;
+                finalizeWindow<R, STEP>(a, wx, wy, sums);
+            }
         }
     }
-}
-
-// arg-min + offset update for windows larger than a CTA tile
-template <int R, int STEP> __global__ void __launch_bounds__(128) finalizeLargeKernel(const SearchArgs a) {
-    const int w = blockIdx.x * blockDim.x + threadIdx.x;
-    if (w >= a.nWx * a.nWy) return;
-    uint32_t sums[R];
-#pragma unroll
-    for (int z = 0; z < R; ++z) sums[z] = a.winSums[(size_t)w * 16 + z];
-    finalizeWindow<R, STEP>(a, w % a.nWx, w / a.nWx, sums);
 }
 
 template <int R> int launchPassR(hrb_ofc* h, const SearchArgs& a, int step, unsigned* launches) {
     const dim3 block(32, 8, 1);
     const int lu = step == 1 ? a.lw : a.lh, lv = step == 1 ? a.lh : a.lw;  // X steps run on the transposed planes (View)
     const dim3 grid((lu + TILE - 1) / TILE, (lv + TILE - 1) / TILE, 1);
-    const bool large = a.ws > TILE;
     bool done = false;
     if (a.rs == 0 && a.ws <= (h->searchVariant == 0 ? 32 : 16) && h->searchVariant != 1) {  // staged small-window kernel (kernels_search_cand.cu)
         const int rc = launchSearchPassCand(h, a, R, step);
@@ -169,9 +184,7 @@ template <int R> int launchPassR(hrb_ofc* h, const SearchArgs& a, int step, unsi
         }
     }
     if (!done) {
-        // generic kernel; windows larger than its tile go through the scratch sums and a finalize kernel.  The scratch
-        // is zeroed before AND after, because the sliding kernels rely on finding it zeroed.
-        if (large) HRB_CUDA(cudaMemsetAsync(a.winSums, 0, (size_t)a.nWx * a.nWy * 16 * sizeof(uint32_t), h->stream));
+        // generic kernel; windows larger than its tile are finalized by the last CTA of each window
         if (step == 0)
             sadPassKernel<R, 0><<<grid, block, 0, h->stream>>>(a);
         else
@@ -179,16 +192,6 @@ template <int R> int launchPassR(hrb_ofc* h, const SearchArgs& a, int step, unsi
         HRB_LAUNCH_CHECK();
     }
     *launches = 1;
-    if (large) {
-        const int nW = a.nWx * a.nWy;
-        if (step == 0)
-            finalizeLargeKernel<R, 0><<<(nW + 127) / 128, 128, 0, h->stream>>>(a);
-        else
-            finalizeLargeKernel<R, 1><<<(nW + 127) / 128, 128, 0, h->stream>>>(a);
-        HRB_LAUNCH_CHECK();
-        HRB_CUDA(cudaMemsetAsync(a.winSums, 0, (size_t)a.nWx * a.nWy * 16 * sizeof(uint32_t), h->stream));
-        *launches = 2;
-    }
     return HRB_OK;
 }
 
