@@ -577,7 +577,12 @@ int hrb_ofc_create(hrb_ofc** out, const hrb_ofc_desc* d) {
     HRB_TRY(cudaEventCreate(&h->warpEndEvent));
     HRB_TRY(cudaEventCreateWithFlags(&h->uploadDoneEvent, cudaEventBlockingSync | cudaEventDisableTiming));
     HRB_TRY(cudaStreamCreateWithFlags(&h->upStream, cudaStreamNonBlocking));
-    HRB_TRY(cudaStreamCreateWithFlags(&h->flowStream, cudaStreamNonBlocking));
+    {
+        // the search ladder is the critical path of a source frame: its CTAs go first when warps compete for the SMs
+        int prioLow = 0, prioHigh = 0;
+        HRB_TRY(cudaDeviceGetStreamPriorityRange(&prioLow, &prioHigh));
+        HRB_TRY(cudaStreamCreateWithPriority(&h->flowStream, cudaStreamNonBlocking, prioHigh));
+    }
     HRB_TRY(cudaEventCreateWithFlags(&h->flowForkEvent, cudaEventDisableTiming));
     HRB_TRY(cudaEventCreateWithFlags(&h->flowJoinEvent, cudaEventDisableTiming));
     h->flowJoinPending = false;
