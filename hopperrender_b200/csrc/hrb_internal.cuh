@@ -194,9 +194,21 @@ int launchWarpFrame(hrb_ofc* h, float t, int mode);
 // kernels_search.cu
 int launchSearchPass(hrb_ofc* h, const SearchArgs& a, int R, int step);
 // kernels_search_big.cu: HRB_OK, an error code, or -1 when this (R, geometry) is not covered
-int launchSearchPassBig(hrb_ofc* h, const SearchArgs& a, int R, int step);
+int launchSearchPassBigPart0(hrb_ofc* h, const SearchArgs& a, int R, int step);  // R 5..8   (kernels_search_big.cu, three builds)
+int launchSearchPassBigPart1(hrb_ofc* h, const SearchArgs& a, int R, int step);  // R 9..12
+int launchSearchPassBigPart2(hrb_ofc* h, const SearchArgs& a, int R, int step);  // R 13..16
+inline int launchSearchPassBig(hrb_ofc* h, const SearchArgs& a, int R, int step) {
+    if (R < 5 || R > 16) return -1;
+    return R <= 8 ? launchSearchPassBigPart0(h, a, R, step) : R <= 12 ? launchSearchPassBigPart1(h, a, R, step) : launchSearchPassBigPart2(h, a, R, step);
+}
 // kernels_search_cand.cu: a whole pass for 2 <= ws <= 16 at full flow resolution; same return convention
-int launchSearchPassCand(hrb_ofc* h, const SearchArgs& a, int R, int step);
+int launchSearchPassCandPart0(hrb_ofc* h, const SearchArgs& a, int R, int step);  // R 5..8   (kernels_search_cand.cu, three builds)
+int launchSearchPassCandPart1(hrb_ofc* h, const SearchArgs& a, int R, int step);  // R 9..12
+int launchSearchPassCandPart2(hrb_ofc* h, const SearchArgs& a, int R, int step);  // R 13..16
+inline int launchSearchPassCand(hrb_ofc* h, const SearchArgs& a, int R, int step) {
+    if (R < 5 || R > 16) return -1;
+    return R <= 8 ? launchSearchPassCandPart0(h, a, R, step) : R <= 12 ? launchSearchPassCandPart1(h, a, R, step) : launchSearchPassCandPart2(h, a, R, step);
+}
 int launchBlurFlow(hrb_ofc* h, const int16_t* lvlX, const int16_t* lvlY, int nWx, int wsLog2, int16_t* out, uint32_t* flowMax);
 int launchExpandOffsets(hrb_ofc* h, const int16_t* lvlX, int nWxX, int wsLog2X, const int16_t* lvlY, int nWxY, int wsLog2Y,
                         int16_t* out);

@@ -336,13 +336,23 @@ template <int R> int launchBigR(hrb_ofc* h, const SearchArgs& a, int step) { ret
 
 }  // namespace
 
-// SAD part of one pass for ws >= 32 at full flow resolution; the caller zeroes winSums before and runs the
-// large-window finalize after when ws > 32.
-int launchSearchPassBig(hrb_ofc* h, const SearchArgs& a, int R, int step) {
+// One whole pass for ws >= 32 at full flow resolution (windows larger than a tile are finalized by their last CTA).
+// Like kernels_search_cand.cu this file is compiled three times (-DHRB_BIG_PART=0/1/2), four search radii per part.
+#ifndef HRB_BIG_PART
+#error "compile with -DHRB_BIG_PART=0, 1 or 2"
+#endif
+#define HRB_BIG_CONCAT2(a, b) a##b
+#define HRB_BIG_CONCAT(a, b) HRB_BIG_CONCAT2(a, b)
+int HRB_BIG_CONCAT(launchSearchPassBigPart, HRB_BIG_PART)(hrb_ofc* h, const SearchArgs& a, int R, int step) {
     switch (R) {
 #define HRB_CASE(N) case N: return launchBigR<N>(h, a, step);
-        HRB_CASE(5) HRB_CASE(6) HRB_CASE(7) HRB_CASE(8) HRB_CASE(9) HRB_CASE(10) HRB_CASE(11) HRB_CASE(12) HRB_CASE(13) HRB_CASE(14)
-        HRB_CASE(15) HRB_CASE(16)
+#if HRB_BIG_PART == 0
+        HRB_CASE(5) HRB_CASE(6) HRB_CASE(7) HRB_CASE(8)
+#elif HRB_BIG_PART == 1
+        HRB_CASE(9) HRB_CASE(10) HRB_CASE(11) HRB_CASE(12)
+#else
+        HRB_CASE(13) HRB_CASE(14) HRB_CASE(15) HRB_CASE(16)
+#endif
 #undef HRB_CASE
         default: return -1;  // not handled here
     }

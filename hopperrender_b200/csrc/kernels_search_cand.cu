@@ -297,11 +297,23 @@ template <int R> int launchCandR(hrb_ofc* h, const SearchArgs& a, int step) {
 }  // namespace
 
 // One whole pass (SAD + arg-min + offset update) for 2 <= ws <= 32 at full flow resolution.
-int launchSearchPassCand(hrb_ofc* h, const SearchArgs& a, int R, int step) {
+// The 12 search radii x 2 steps x 2 (taps) x 5 window sizes are 240 kernels: this file is compiled three times
+// (-DHRB_CAND_PART=0/1/2, see the Makefile), each part instantiating four radii, so the parts build in parallel.
+#ifndef HRB_CAND_PART
+#error "compile with -DHRB_CAND_PART=0, 1 or 2"
+#endif
+#define HRB_CAND_CONCAT2(a, b) a##b
+#define HRB_CAND_CONCAT(a, b) HRB_CAND_CONCAT2(a, b)
+int HRB_CAND_CONCAT(launchSearchPassCandPart, HRB_CAND_PART)(hrb_ofc* h, const SearchArgs& a, int R, int step) {
     switch (R) {
 #define HRB_CASE(N) case N: return launchCandR<N>(h, a, step);
-        HRB_CASE(5) HRB_CASE(6) HRB_CASE(7) HRB_CASE(8) HRB_CASE(9) HRB_CASE(10) HRB_CASE(11) HRB_CASE(12) HRB_CASE(13) HRB_CASE(14)
-        HRB_CASE(15) HRB_CASE(16)
+#if HRB_CAND_PART == 0
+        HRB_CASE(5) HRB_CASE(6) HRB_CASE(7) HRB_CASE(8)
+#elif HRB_CAND_PART == 1
+        HRB_CASE(9) HRB_CASE(10) HRB_CASE(11) HRB_CASE(12)
+#else
+        HRB_CASE(13) HRB_CASE(14) HRB_CASE(15) HRB_CASE(16)
+#endif
 #undef HRB_CASE
         default: return -1;
     }
