@@ -209,7 +209,7 @@ def run_reference(args, wl, wl_name):
     if rank != 0:
         return
     cores = num_threads()
-    per_step = max(1.0, min(8.0, float(os.environ.get("HRB_REF_BUDGET_S", "150")) / max(args.steps + args.warmup, 1)))
+    per_step = max(0.2, min(8.0, float(os.environ.get("HRB_REF_BUDGET_S", "150")) / max(args.steps + args.warmup, 1)))
     rows = cpu_sample_rows(wl, per_step)
     step = cpu_step_runner(wl, rows)
     for _ in range(args.warmup):
