@@ -11,7 +11,8 @@
 namespace hrb {
 
 static thread_local std::string t_lastError;
-unsigned long long g_launchCount = 0;
+std::atomic<unsigned long long> g_launchCount{0};
+thread_local unsigned long long t_launchCount = 0;
 
 void setLastError(const char* fmt, ...) {
     char buf[512];
@@ -263,7 +264,7 @@ static int launchFlowKernels(hrb_ofc* h, int R, int ws0, int iterations) {
             hit = &g;
     if (!hit) {
         if (h->flowGraphs.size() >= 32) dropFlowGraphs(h);  // parameters keep changing (auto-tuner, UI): start over
-        const unsigned long long before = g_launchCount;
+        const unsigned long long before = t_launchCount;
         if (cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal) != cudaSuccess) {
             cudaGetLastError();
             h->flowGraphsOn = false;  // e.g. the caller's stream is the legacy default stream
@@ -272,8 +273,8 @@ static int launchFlowKernels(hrb_ofc* h, int R, int ws0, int iterations) {
         const int rc = issueFlowKernels(h, R, ws0, iterations, true);
         cudaGraph_t graph = nullptr;
         const cudaError_t ce = cudaStreamEndCapture(h->stream, &graph);
-        key.launches = (unsigned)(g_launchCount - before);
-        g_launchCount = before;  // nothing has run yet
+        key.launches = (unsigned)(t_launchCount - before);
+        g_launchCount.fetch_sub(key.launches, std::memory_order_relaxed);  // captured, not run yet
         key.exec = nullptr;
         if (rc == HRB_OK && ce == cudaSuccess && graph && cudaGraphInstantiate(&key.exec, graph, 0) == cudaSuccess) {
             cudaGraphDestroy(graph);
@@ -291,7 +292,7 @@ static int launchFlowKernels(hrb_ofc* h, int R, int ws0, int iterations) {
         if (rc) return rc;
     }
     HRB_CUDA(cudaGraphLaunch(hit->exec, h->stream));
-    g_launchCount += hit->launches;
+    g_launchCount.fetch_add(hit->launches, std::memory_order_relaxed);
     return HRB_OK;
 }
 
@@ -1070,7 +1071,7 @@ int hrb_ofc_set_search_variant(hrb_ofc* h, int variant) {
     return HRB_OK;
 }
 
-uint64_t hrb_kernel_launch_count(void) { return g_launchCount; }
+uint64_t hrb_kernel_launch_count(void) { return g_launchCount.load(std::memory_order_relaxed); }
 
 int hrb_microbench_sad_peak(int device_ordinal, double* giga_absdiff_per_s) {
     HRB_REQUIRE(giga_absdiff_per_s, "null argument");

@@ -4,6 +4,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <atomic>
 #include <string>
 #include <vector>
 
@@ -16,7 +17,9 @@ namespace hrb {
 // the C++ shim in include/opticalFlowCalc.h re-throws)
 // ------------------------------------------------------------------------------------------------
 void setLastError(const char* fmt, ...);
-extern unsigned long long g_launchCount;
+extern std::atomic<unsigned long long> g_launchCount;  // kernels launched by this process (handles may live on several threads)
+extern thread_local unsigned long long t_launchCount;     // ... by this thread: lets a graph capture count its own nodes
+constexpr int HRB_MAX_DEVICES = 64;  // per-device launch configuration caches (power of two)
 
 #define HRB_CUDA(call)                                                                                   \
     do {                                                                                                 \
@@ -30,7 +33,8 @@ extern unsigned long long g_launchCount;
 
 #define HRB_LAUNCH_CHECK()                                                                               \
     do {                                                                                                 \
-        ::hrb::g_launchCount++;                                                                          \
+        ::hrb::g_launchCount.fetch_add(1, std::memory_order_relaxed);                                     \
+        ::hrb::t_launchCount++;                                                                          \
         HRB_CUDA(cudaGetLastError());                                                                    \
     } while (0)
 

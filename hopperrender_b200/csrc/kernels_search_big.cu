@@ -281,7 +281,8 @@ template <int R, int STEP, int NW> __global__ void __launch_bounds__(32 * NW) sa
 
 template <int R, int STEP, int NW> int launchSlidePipe(hrb_ofc* h, const SearchArgs& a, int lu, int lv) {
     constexpr size_t BYTES = 2 * (size_t)(32 * NW + CandSpan<R>::SPAN) * SSP * 4;
-    static int perSm = 0;
+    static int perSmOf[HRB_MAX_DEVICES] = {};  // per device: the shared-memory attribute belongs to the function on one device
+    int& perSm = perSmOf[h->device & (HRB_MAX_DEVICES - 1)];
     if (perSm == 0) {
         HRB_CUDA(cudaFuncSetAttribute(sadSlidePipeKernel<R, STEP, NW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BYTES));
         if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, sadSlidePipeKernel<R, STEP, NW>, 32 * NW, BYTES) != cudaSuccess || perSm < 1) perSm = 1;
@@ -294,10 +295,10 @@ template <int R, int STEP, int NW> int launchSlidePipe(hrb_ofc* h, const SearchA
 
 template <int R, int STEP, int NW, int WU> int launchSlideStaged(hrb_ofc* h, const SearchArgs& a, int lu, int lv) {
     constexpr size_t BYTES = (size_t)(32 * NW + CandSpan<R>::SPAN) * (32 * WU + 4) * 4;
-    static bool configured = false;
-    if (!configured) {
+    static bool configured[HRB_MAX_DEVICES] = {};  // the attribute is per device
+    if (!configured[h->device & (HRB_MAX_DEVICES - 1)]) {
         HRB_CUDA(cudaFuncSetAttribute(sadSlideStagedKernel<R, STEP, NW, WU>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BYTES));
-        configured = true;
+        configured[h->device & (HRB_MAX_DEVICES - 1)] = true;
     }
     sadSlideStagedKernel<R, STEP, NW, WU><<<dim3((lu + 32 * WU - 1) / (32 * WU), (lv + 32 * NW - 1) / (32 * NW), 1), dim3(32, NW * WU, 1), BYTES, h->stream>>>(a);
     return HRB_OK;

@@ -265,10 +265,10 @@ template <int R, int STEP, bool TAPS, int WS> __global__ void __launch_bounds__(
 }
 
 template <int R, int STEP, bool TAPS, int WS> int launchCandOne(hrb_ofc* h, const SearchArgs& a) {
-    static bool configured = false;
-    if (!configured) {
+    static bool configured[HRB_MAX_DEVICES] = {};  // the attribute is per device
+    if (!configured[h->device & (HRB_MAX_DEVICES - 1)]) {
         HRB_CUDA(cudaFuncSetAttribute(sadCandKernel<R, STEP, TAPS, WS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)candSmem<WS>()));
-        configured = true;
+        configured[h->device & (HRB_MAX_DEVICES - 1)] = true;
     }
     const int lu = STEP == 1 ? a.lw : a.lh, lv = STEP == 1 ? a.lh : a.lw;
     const dim3 grid((lu + CT_U - 1) / CT_U, (lv + CT_V - 1) / CT_V, 1);
