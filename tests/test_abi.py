@@ -52,3 +52,21 @@ def test_product_does_not_reference_the_oracle():
                     if fn == "_lib.py" and re.search(r"import\s+oracle|from\s+oracle", txt):
                         bad.append(os.path.join(dp, fn))
     assert not bad, bad
+
+
+def test_cpp_shim_compiles_and_links_against_the_library(tmp_path):
+    """include/opticalFlowCalc*.h are the classes a HopperRender build would include instead of the reference's: the
+    delivery-loop driver written against the reference's class surface must compile and link with nothing else."""
+    import subprocess
+    exe = tmp_path / "replay_check.bin"
+    cmd = ["/usr/bin/g++", "-O1", "-std=c++17", "-Wall", "-Werror", "-I" + os.path.join(ROOT, "include"), os.path.join(ROOT, "tools", "replay.cpp"),
+           "-o", str(exe), "-L" + os.path.join(ROOT, "hopperrender_b200"), "-lhrb", "-Wl,-rpath," + os.path.join(ROOT, "hopperrender_b200")]
+    res = subprocess.run(cmd, capture_output=True, text=True)
+    assert res.returncode == 0, res.stderr
+    # no device here: the program must fail loudly (exception text from hrb_last_error), not fall back to anything
+    raw = tmp_path / "f.raw"
+    raw.write_bytes(bytes(64 * 48 * 3 // 2 * 3))
+    run = subprocess.run([str(exe), str(raw), "64", "48", "0", "3", "166667", "270", "8"], capture_output=True, text=True)
+    import torch
+    if not torch.cuda.is_available():
+        assert run.returncode != 0
