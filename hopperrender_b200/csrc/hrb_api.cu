@@ -437,6 +437,14 @@ int hrb_ofc_create(hrb_ofc** out, const hrb_ofc_desc* d) {
     HRB_REQUIRE(d->frame_width >= 16 && d->frame_height >= 16, "frame must be at least 16x16");
     HRB_REQUIRE((d->frame_width % 2) == 0 && (d->frame_height % 2) == 0, "NV12/P010 frame dimensions must be even");
     HRB_REQUIRE(d->max_calc_res >= 1, "max_calc_res must be positive");
+    HRB_REQUIRE(d->input_stride <= 0 || d->input_stride >= d->frame_width, "stride smaller than the frame width");
+    HRB_REQUIRE(d->output_stride <= 0 || d->output_stride >= d->frame_width, "stride smaller than the frame width");
+    {
+        int rs = 0;
+        while ((d->frame_height >> rs) > d->max_calc_res) rs++;
+        HRB_REQUIRE((d->frame_width >> rs) >= 4 && (d->frame_height >> rs) >= 4, "flow resolution below 4x4 (raise max_calc_res)");
+    }
+    HRB_REQUIRE(d->delta_scalar >= 0 && d->delta_scalar <= 31 && d->neighbor_scalar >= 0 && d->neighbor_scalar <= 31, "delta/neighbor scalar outside 0..31");
     int nDev = 0;
     if (cudaGetDeviceCount(&nDev) != cudaSuccess || nDev == 0) {
         setLastError("[hopperrender_b200] no CUDA device (this library has no CPU fallback)");

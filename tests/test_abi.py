@@ -70,3 +70,38 @@ def test_cpp_shim_compiles_and_links_against_the_library(tmp_path):
     import torch
     if not torch.cuda.is_available():
         assert run.returncode != 0
+
+
+@pytest.mark.parametrize("kw,needle", [
+    (dict(frameHeight=0, frameWidth=0), "at least 16x16"),            # empty frame
+    (dict(frameHeight=8, frameWidth=64), "at least 16x16"),
+    (dict(frameHeight=48, frameWidth=63), "must be even"),            # NV12/P010 need even dimensions
+    (dict(frameHeight=49, frameWidth=64), "must be even"),
+    (dict(inputStride=32), "stride smaller"),                         # ragged: stride below the width
+    (dict(outputStride=63), "stride smaller"),
+    (dict(maxCalcRes=0), "max_calc_res"),
+    (dict(frameHeight=4096, frameWidth=16, maxCalcRes=16), "below 4x4"),
+    (dict(deltaScalar=32), "scalar outside"),
+    (dict(neighborScalar=-1), "scalar outside"),
+])
+def test_create_rejects_bad_geometry_before_touching_the_device(kw, needle):
+    """Argument errors are reported as such (HRB_ERR_INVALID_ARG with a message), with or without a GPU."""
+    import hopperrender_b200 as hr
+    args = dict(frameHeight=48, frameWidth=64, inputStride=0, outputStride=0, deltaScalar=8, neighborScalar=6, blackLevel=0.0,
+                whiteLevel=255.0, maxCalcRes=270)
+    args.update(kw)
+    with pytest.raises(RuntimeError) as e:
+        hr.OpticalFlowCalcSDR(args["frameHeight"], args["frameWidth"], args["inputStride"], args["outputStride"], args["deltaScalar"],
+                              args["neighborScalar"], args["blackLevel"], args["whiteLevel"], args["maxCalcRes"])
+    assert "hrb error 1" in str(e.value) and needle in str(e.value)
+
+
+def test_null_handles_and_pointers_are_argument_errors():
+    from hopperrender_b200 import _lib
+    lib = _lib.load()
+    assert lib.hrb_ofc_update_frame(None, None) == 1
+    assert lib.hrb_ofc_calculate_optical_flow(None) == 1
+    assert lib.hrb_ofc_warp_frames(None, 0.5, 2) == 1
+    assert lib.hrb_ofc_download_frame(None, None) == 1
+    assert lib.hrb_ofc_create(None, None) == 1
+    assert b"null" in lib.hrb_last_error()
