@@ -263,7 +263,7 @@ static int launchFlowKernels(hrb_ofc* h, int R, int ws0, int iterations) {
             g.neighborBiasScalar == key.neighborBiasScalar && g.variant == key.variant)
             hit = &g;
     if (!hit) {
-        if (h->flowGraphs.size() >= 32) dropFlowGraphs(h);  // parameters keep changing (auto-tuner, UI): start over
+        if (h->flowGraphs.size() >= 64) dropFlowGraphs(h);  // 12 radii x 4 slot rotations fit; beyond that parameters keep changing (UI): start over
         const unsigned long long before = t_launchCount;
         if (cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal) != cudaSuccess) {
             cudaGetLastError();
