@@ -105,3 +105,21 @@ def test_null_handles_and_pointers_are_argument_errors():
     assert lib.hrb_ofc_download_frame(None, None) == 1
     assert lib.hrb_ofc_create(None, None) == 1
     assert b"null" in lib.hrb_last_error()
+
+
+def test_header_is_plain_c_and_the_c_example_builds(tmp_path):
+    """include/hrb.h is the FFI surface: it must compile as pedantic C99 (no C++-isms, no torch/CUDA types), and the C
+    example of the call sequence must link against the library alone."""
+    import subprocess
+    exe = tmp_path / "example_c"
+    cmd = ["/usr/bin/gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-I" + os.path.join(ROOT, "include"),
+           os.path.join(ROOT, "tools", "example_c_api.c"), "-o", str(exe), "-L" + os.path.join(ROOT, "hopperrender_b200"), "-lhrb",
+           "-Wl,-rpath," + os.path.join(ROOT, "hopperrender_b200")]
+    res = subprocess.run(cmd, capture_output=True, text=True)
+    assert res.returncode == 0, res.stderr
+    run = subprocess.run([str(exe)], capture_output=True, text=True)
+    import torch
+    if torch.cuda.is_available():
+        assert run.returncode == 0 and "flow 160x90" in run.stdout, run.stdout + run.stderr
+    else:
+        assert run.returncode == 2 and "no CUDA device" in run.stderr
