@@ -120,6 +120,6 @@ def test_header_is_plain_c_and_the_c_example_builds(tmp_path):
     run = subprocess.run([str(exe)], capture_output=True, text=True)
     import torch
     if torch.cuda.is_available():
-        assert run.returncode == 0 and "flow 160x90" in run.stdout, run.stdout + run.stderr
+        assert run.returncode == 0 and "flow 320x180" in run.stdout, run.stdout + run.stderr
     else:
         assert run.returncode == 2 and "no CUDA device" in run.stderr
