@@ -68,6 +68,16 @@ class OracleAsCalc:
     m_ofcCalcTime = property(lambda s: s._o.state().ofcCalcTime)
     m_warpCalcTime = property(lambda s: s._o.state().warpCalcTime)
     m_opticalFlowSearchRadius = property(lambda s: s._o.state().searchRadius, lambda s, v: s._o.setParams(searchRadius=int(v)))
+    m_ofcAvgCalcTime = property(lambda s: s._o.state().ofcAvgCalcTime)
+    m_ofcPeakCalcTime = property(lambda s: s._o.state().ofcPeakCalcTime)
+    m_frameWidth = property(lambda s: s._o.state().frameWidth)
+    m_frameHeight = property(lambda s: s._o.state().frameHeight)
+    m_opticalFlowFrameWidth = property(lambda s: s._o.state().flowWidth)
+    m_opticalFlowFrameHeight = property(lambda s: s._o.state().flowHeight)
+    m_deltaScalar = property(lambda s: s._o.state().deltaScalar, lambda s, v: s._o.setParams(deltaScalar=int(v)))
+    m_neighborBiasScalar = property(lambda s: s._o.state().neighborBiasScalar, lambda s, v: s._o.setParams(neighborBiasScalar=int(v)))
+    m_outputBlackLevel = property(lambda s: s._o.state().outputBlackLevel, lambda s, v: s._o.setParams(black=float(v)))
+    m_outputWhiteLevel = property(lambda s: s._o.state().outputWhiteLevel, lambda s, v: s._o.setParams(white=float(v)))
 
 
 def oob_windows(offs, ws, R, step, W, H, rs):
