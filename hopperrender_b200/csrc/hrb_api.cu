@@ -141,11 +141,11 @@ static int issueFlowKernels(hrb_ofc* h, int R, int ws0, int iterations, bool iss
     const int lw = h->flowWidth, lh = h->flowHeight;
     SearchArgs a;
     memset(&a, 0, sizeof(a));
-    a.plane1 = h->searchPlane[1];  // frame1 = m_inputFrameArray[1], opticalFlowCalcSDR.cpp:79
-    a.plane2 = h->searchPlane[2];  // frame2 = m_inputFrameArray[2], opticalFlowCalcSDR.cpp:80
+    const SearchPlanes& f1 = h->searchPlane[1];  // frame1 = m_inputFrameArray[1], opticalFlowCalcSDR.cpp:79
+    const SearchPlanes& f2 = h->searchPlane[2];  // frame2 = m_inputFrameArray[2], opticalFlowCalcSDR.cpp:80
+    a.y1 = f1.y; a.c1 = f1.c; a.yT1 = f1.yT; a.cT1 = f1.cT;
+    a.y2 = f2.y; a.c2 = f2.c; a.yT2 = f2.yT; a.cT2 = f2.cT;
     a.pitch = h->planePitch;
-    a.planeT1 = h->searchPlaneT[1];
-    a.planeT2 = h->searchPlaneT[2];
     a.pitchT = h->planePitchT;
     a.W = h->frameWidth;
     a.H = h->frameHeight;
@@ -250,8 +250,8 @@ static void dropFlowGraphs(hrb_ofc* h) {
 static int launchFlowKernels(hrb_ofc* h, int R, int ws0, int iterations) {
     if (!h->flowGraphsOn || h->tapMode || h->prof.on) return issueFlowKernels(h, R, ws0, iterations, true);
     hrb_ofc::FlowGraph key;
-    key.plane1 = h->searchPlane[1];
-    key.plane2 = h->searchPlane[2];
+    key.plane1 = h->searchPlane[1].base;
+    key.plane2 = h->searchPlane[2].base;
     key.blurOut = h->blurredOffsetArray[0];
     key.R = R;
     key.deltaScalar = h->deltaScalar;
@@ -348,11 +348,20 @@ static int finishUpdate(hrb_ofc* h) {
         v[3] = f0;
     };
     rot(h->inputFrameArray);
-    rot(h->searchPlane);
-    rot(h->searchPlaneT);
+    {
+        const SearchPlanes s0 = h->searchPlane[0];
+        h->searchPlane[0] = h->searchPlane[1];
+        h->searchPlane[1] = h->searchPlane[2];
+        h->searchPlane[2] = h->searchPlane[3];
+        h->searchPlane[3] = s0;
+    }
     h->frameCount++;
     // every reader of the buffer that just became slot [3] (the warps of the previous source frame) is already enqueued
     HRB_CUDA(cudaEventRecord(h->spareFreeEvent, h->stream));
+    // an asynchronous flow still in flight reads the search planes of slots [1] and [2] as they were when it was
+    // enqueued; three updates later the ingest writes one of them.  Order the ingest behind it (free in steady state:
+    // the next calculate joins anyway).
+    if (h->flowJoinPending) HRB_CUDA(cudaStreamWaitEvent(h->stream, h->flowJoinEvent, 0));
     return launchPackFrame(h, 2);
 }
 
@@ -501,8 +510,7 @@ int hrb_ofc_create(hrb_ofc** out, const hrb_ofc_desc* d) {
     h->lastNWx = h->lastNWy = h->lastWs = 0;
     for (int i = 0; i < 4; ++i) {
         h->inputFrameArray[i] = nullptr;
-        h->searchPlane[i] = nullptr;
-        h->searchPlaneT[i] = nullptr;
+        h->searchPlane[i] = SearchPlanes();
     }
     for (int i = 0; i < hrb_ofc::kOutRing; ++i) {
         h->outputRing[i] = nullptr;
@@ -541,10 +549,13 @@ int hrb_ofc_create(hrb_ofc** out, const hrb_ofc_desc* d) {
     const size_t lw = h->flowWidth, lh = h->flowHeight;
     h->inFrameBytes = ((size_t)h->frameHeight * h->inputStride + (size_t)(h->frameHeight / 2) * h->inputStride) * h->bpp;
     h->outFrameBytes = ((size_t)h->frameHeight * h->outputStride + (size_t)(h->frameHeight / 2) * h->outputStride) * h->bpp;
-    h->planePitch = (h->frameWidth + 31) & ~31;
-    const size_t planeBytes = (size_t)h->planePitch * h->frameHeight * sizeof(uint32_t);
-    h->planePitchT = (h->frameHeight + 31) & ~31;
-    const size_t planeTBytes = (size_t)h->planePitchT * h->frameWidth * sizeof(uint32_t);
+    // planar 8-bit search planes: luma + NV12-style chroma, row-major and transposed (rows padded to 128 bytes: the
+    // TMA row stride must be a multiple of 16 and a warp's 128-byte row segment never leaves the allocation)
+    h->planePitch = (h->frameWidth + 127) & ~127;
+    h->planePitchT = (h->frameHeight + 127) & ~127;
+    const size_t planeYBytes = (size_t)h->planePitch * h->frameHeight, planeCBytes = (size_t)h->planePitch * (h->frameHeight / 2);
+    const size_t planeYTBytes = (size_t)h->planePitchT * h->frameWidth, planeCTBytes = (size_t)h->planePitchT * (h->frameWidth / 2);
+    const size_t planeBytes = planeYBytes + planeCBytes + 256, planeTBytes = planeYTBytes + planeCTBytes + 256;
     h->levelCapacity = ((lw + 1) / 2) * ((lh + 1) / 2);
     const size_t winSumEntries = ((lw + 63) / 64) * ((lh + 63) / 64) * 16 + 16;
     const size_t need = 4 * (h->inFrameBytes + planeBytes + planeTBytes) + 3 * h->outFrameBytes + 4 * h->levelCapacity * 2 + winSumEntries * 4 + 3 * 2 * lw * lh * 2;
@@ -608,10 +619,13 @@ int hrb_ofc_create(hrb_ofc** out, const hrb_ofc_desc* d) {
     for (int i = 0; i < 4; ++i) {
         HRB_TRY(cudaMalloc(&h->inputFrameArray[i], h->inFrameBytes));
         HRB_TRY(cudaMemsetAsync(h->inputFrameArray[i], 0, h->inFrameBytes, h->stream));
-        HRB_TRY(cudaMalloc(&h->searchPlane[i], planeBytes));
-        HRB_TRY(cudaMemsetAsync(h->searchPlane[i], 0, planeBytes, h->stream));
-        HRB_TRY(cudaMalloc(&h->searchPlaneT[i], planeTBytes));
-        HRB_TRY(cudaMemsetAsync(h->searchPlaneT[i], 0, planeTBytes, h->stream));
+        SearchPlanes& sp = h->searchPlane[i];
+        HRB_TRY(cudaMalloc(&sp.base, planeBytes + planeTBytes));
+        HRB_TRY(cudaMemsetAsync(sp.base, 0, planeBytes + planeTBytes, h->stream));
+        sp.y = sp.base;                       // cudaMalloc returns 256-byte aligned memory; every plane starts 128-byte aligned
+        sp.c = sp.y + planeYBytes;
+        sp.yT = sp.c + planeCBytes + 256;       // plane sizes are multiples of 128 (padded pitches)
+        sp.cT = sp.yT + planeYTBytes;
     }
     for (int p = 0; p < 2; ++p)
         for (int ax = 0; ax < 2; ++ax) {
@@ -652,8 +666,7 @@ void hrb_ofc_destroy(hrb_ofc* h) {
     for (auto e : h->prof.pool) cudaEventDestroy(e);
     for (int i = 0; i < 4; ++i) {
         cudaFree(h->inputFrameArray[i]);
-        cudaFree(h->searchPlane[i]);
-        cudaFree(h->searchPlaneT[i]);
+        cudaFree(h->searchPlane[i].base);
     }
     for (int i = 0; i < hrb_ofc::kOutRing; ++i) {
         cudaFree(h->outputRing[i]);
@@ -664,6 +677,7 @@ void hrb_ofc_destroy(hrb_ofc* h) {
         if (e) cudaEventDestroy(e);
     if (h->spareFreeEvent) cudaEventDestroy(h->spareFreeEvent);
     dropFlowGraphs(h);
+    freeTmaCache(h);
     if (h->upStream) cudaStreamDestroy(h->upStream);
     if (h->flowStream) cudaStreamDestroy(h->flowStream);
     if (h->flowForkEvent) cudaEventDestroy(h->flowForkEvent);
@@ -807,7 +821,8 @@ int hrb_ofc_wait_download(hrb_ofc* h, unsigned long long ticket) {
     HRB_REQUIRE(h, "null handle");
     HRB_REQUIRE(ticket >= 1 && ticket <= h->downloadSeq, "unknown ticket");
     HRB_CUDA(cudaSetDevice(h->device));
-    if (h->downloadSeq - ticket >= (unsigned long long)hrb_ofc::kTickets) return HRB_OK;  // its event was reused, i.e. it completed long ago
+    // The slot may have been re-recorded by a later download (tickets wrap every kTickets): the download stream is in
+    // order, so waiting for that later record also proves that this ticket's copy has landed.  Never return unwaited.
     HRB_CUDA(cudaEventSynchronize(h->ticketEvent[ticket % hrb_ofc::kTickets]));
     return HRB_OK;
 }
@@ -1073,7 +1088,7 @@ int hrb_ofc_join_flow(hrb_ofc* h) {
 
 int hrb_ofc_set_search_variant(hrb_ofc* h, int variant) {
     HRB_REQUIRE(h, "null handle");
-    HRB_REQUIRE(variant >= 0 && variant <= 3, "variant must be 0 (automatic), 1 (generic kernels only), 2 (L1-fed sliding kernel) or 3 (persistent double-buffered sliding kernel)");
+    HRB_REQUIRE(variant >= 0 && variant <= 3, "variant must be 0 (automatic), 1 (generic kernels only), 2 (sliding kernel staged without TMA) or 3 (sliding kernel without the aligned fast path)");
     h->searchVariant = variant;
     h->warpVariant = variant == 1 ? 1 : 0;
     return HRB_OK;

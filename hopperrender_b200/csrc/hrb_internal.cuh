@@ -53,12 +53,14 @@ struct PassGeom {
 // Arguments of the search kernels.  Window-level offset arrays replace the per-pixel offsetArray of the
 // reference (offsets are constant inside each window).
 struct SearchArgs {
-    const uint32_t* plane1;  // search plane of frame N-1 (m_inputFrameArray[1]): {Y,U,V,0} per luma pixel
-    const uint32_t* plane2;  // search plane of frame N   (m_inputFrameArray[2])
-    int pitch;               // words per search-plane row
-    const uint32_t* planeT1; // the same planes transposed ([x][y]); X steps read these
-    const uint32_t* planeT2;
-    int pitchT;              // words per transposed row (>= H)
+    // 8-bit search planes (HDR samples >> 8, calcDeltaSumsKernelHDR.h:98-100) of frame N-1 (m_inputFrameArray[1], "1")
+    // and frame N (m_inputFrameArray[2], "2"): luma [H][pitch] and the interleaved U,V plane [H/2][pitch] in the
+    // NV12 layout; the T planes are the same data transposed, luma [W][pitchT] and chroma [W/2][pitchT] with
+    // byte 2*(y>>1)+ch of row x>>1 = channel ch of chroma sample (y>>1, x>>1).  X steps read the T planes.
+    const uint8_t *y1, *c1, *y2, *c2;
+    const uint8_t *yT1, *cT1, *yT2, *cT2;
+    int pitch;               // bytes per row of y / c (multiple of 128)
+    int pitchT;              // bytes per row of yT / cT (multiple of 128)
     int W, H;                // frame size
     int lw, lh;              // flow size
     int rs;                  // resolution scalar
@@ -75,6 +77,14 @@ struct SearchArgs {
     uint32_t* tapSums;     // optional [R][nWy][nWx]
     uint8_t* tapLayer;     // optional [nWy][nWx]
 };
+
+// The search representation of one input slot: 8-bit planes in both orientations, one allocation.
+struct SearchPlanes {
+    uint8_t* base = nullptr;   // the allocation
+    uint8_t *y = nullptr, *c = nullptr, *yT = nullptr, *cT = nullptr;
+};
+
+struct TmaCache;
 
 struct PassTapDev {
     PassGeom g;
@@ -150,10 +160,9 @@ struct hrb_ofc {
     // device arrays
     size_t inFrameBytes, outFrameBytes;
     uint8_t* inputFrameArray[4];   // raw NV12 / P010 frames, [0..2] rotated like m_inputFrameArray, [3] = upload target
-    uint32_t* searchPlane[4];      // packed 8-bit search representation of the same slot
-    int planePitch;                // words
-    uint32_t* searchPlaneT[4];     // transposed copy of searchPlane (X steps read these so that their accesses are row segments too)
-    int planePitchT;               // words
+    hrb::SearchPlanes searchPlane[4];  // 8-bit planar search representation of the same slot (row-major + transposed)
+    int planePitch;                // bytes per row of the row-major planes
+    int planePitchT;               // bytes per row of the transposed planes
     int stripeY0, stripeY1;        // output stripe (luma rows) warpFrames / copyFrame / downloadFrame work on; default the whole frame
     uint8_t* outputRing[3];        // m_outputFrameArray, as a ring so that a download can overlap the next warp
     int16_t* levelOffsets[2][2];   // [iteration parity][axis] window-level offsets
@@ -169,7 +178,7 @@ struct hrb_ofc {
     bool haveFlowLevels;
 
     // taps / profiling
-    int searchVariant;  // 0: automatic kernel selection, 1: generic sadPassKernel for every pass (A/B and parity tests)
+    int searchVariant;  // 0: automatic kernel selection, 1: generic sadPassKernel for every pass, 2: sliding kernel without TMA, 3: ... without the aligned fast path
     int warpVariant;    // 0: automatic (table-driven fast kernel for modes 0-2), 1: generic warpFrameKernel for every mode
     int smCount;
     bool tapMode;
@@ -187,6 +196,7 @@ struct hrb_ofc {
     bool flowGraphsOn;
     std::vector<hrb::PassTapDev> taps;
     hrb::Profile prof;
+    hrb::TmaCache* tmaCache = nullptr;  // TMA descriptors of the search planes, encoded on first use
 };
 
 namespace hrb {
@@ -197,14 +207,15 @@ int launchCopyFrame(hrb_ofc* h, int slot);
 int launchWarpFrame(hrb_ofc* h, float t, int mode);
 // kernels_search.cu
 int launchSearchPass(hrb_ofc* h, const SearchArgs& a, int R, int step);
-// kernels_search_big.cu: HRB_OK, an error code, or -1 when this (R, geometry) is not covered
-int launchSearchPassBigPart0(hrb_ofc* h, const SearchArgs& a, int R, int step);  // R 5..8   (kernels_search_big.cu, three builds)
-int launchSearchPassBigPart1(hrb_ofc* h, const SearchArgs& a, int R, int step);  // R 9..12
-int launchSearchPassBigPart2(hrb_ofc* h, const SearchArgs& a, int R, int step);  // R 13..16
-inline int launchSearchPassBig(hrb_ofc* h, const SearchArgs& a, int R, int step) {
+// kernels_search_slide.cu: HRB_OK, an error code, or -1 when this (R, geometry) is not covered
+int launchSearchPassSlidePart0(hrb_ofc* h, const SearchArgs& a, int R, int step);  // R 5..8   (kernels_search_slide.cu, three builds)
+int launchSearchPassSlidePart1(hrb_ofc* h, const SearchArgs& a, int R, int step);  // R 9..12
+int launchSearchPassSlidePart2(hrb_ofc* h, const SearchArgs& a, int R, int step);  // R 13..16
+inline int launchSearchPassSlide(hrb_ofc* h, const SearchArgs& a, int R, int step) {
     if (R < 5 || R > 16) return -1;
-    return R <= 8 ? launchSearchPassBigPart0(h, a, R, step) : R <= 12 ? launchSearchPassBigPart1(h, a, R, step) : launchSearchPassBigPart2(h, a, R, step);
+    return R <= 8 ? launchSearchPassSlidePart0(h, a, R, step) : R <= 12 ? launchSearchPassSlidePart1(h, a, R, step) : launchSearchPassSlidePart2(h, a, R, step);
 }
+void freeTmaCache(hrb_ofc* h);  // tensor maps of the handle's search planes (kernels_search_slide.cu)
 // kernels_search_cand.cu: a whole pass for 2 <= ws <= 16 at full flow resolution; same return convention
 int launchSearchPassCandPart0(hrb_ofc* h, const SearchArgs& a, int R, int step);  // R 5..8   (kernels_search_cand.cu, three builds)
 int launchSearchPassCandPart1(hrb_ofc* h, const SearchArgs& a, int R, int step);  // R 9..12

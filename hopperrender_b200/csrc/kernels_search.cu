@@ -3,8 +3,9 @@
 // One search pass = calcDeltaSumsKernel + determineLowestLayerKernel + adjustOffsetArrayKernel of the
 // reference (HopperRender/opticalFlowCalcSDR.cpp:72-107) for one (iteration, step).  The design uses
 // three facts:
-//   * the search only looks at 8-bit data, so both frames are pre-packed into {Y,U,V,0} words and one
-//     VABSDIFF4.U8.ACC evaluates the reference's 3-term delta for one pixel-candidate;
+//   * the search only looks at 8-bit data, so both frames are kept as 8-bit planes (luma + NV12-style chroma, in both
+//     orientations); the generic kernel below assembles {Y,U,V,0} words, so that one VABSDIFF4.U8.ACC evaluates the
+//     reference's 3-term delta for one pixel-candidate, the specialised kernels work on the planes directly;
 //   * offsets are constant inside each aligned window, so they live in per-window arrays and the
 //     offset / neighbour bias of a window is (pixel count) x (a per-window constant);
 //   * sums are uint32 modulo 2^32, so any summation order is bit-exact.
@@ -51,21 +52,20 @@ template <int R, int STEP> __global__ void __launch_bounds__(256) sadPassKernel(
         if (pixOk) {
             const int su = cu << a.rs;
             const int ou = View<STEP>::ou(ox, oy), ov = View<STEP>::ov(ox, oy);
-            const uint32_t* __restrict__ col = vw.p1 + mirrorSearch(su + ou, vw.dimU);
+            const int fu = mirrorSearch(su + ou, vw.dimU);  // frame-1 column of this lane
             for (int r = 0; r < gh; ++r) {
                 const int cv = cv0 + r;
                 if (cv >= vw.lv) break;
                 const int sv = cv << a.rs;
-                const uint32_t f2 = __ldg(rowPtr(vw.p2 + su, vw.pitch, sv));
+                const uint32_t f2 = fetchPixel(vw.y2, vw.c2, vw.pitch, sv, su);
                 const int bv = sv + ov;
                 if (bv + LO >= 0 && bv + HI < vw.dimV) {
-                    const uint32_t* __restrict__ p = rowPtr(col, vw.pitch, bv);
 #pragma unroll
-                    for (int z = 0; z < R; ++z) acc[z] = sad4(__ldg(rowPtr(p, vw.pitch, candOffset<R>(z))), f2, acc[z]);
+                    for (int z = 0; z < R; ++z) acc[z] = sad4(fetchPixel(vw.y1, vw.c1, vw.pitch, bv + candOffset<R>(z), fu), f2, acc[z]);
                 } else {
 #pragma unroll
                     for (int z = 0; z < R; ++z)
-                        acc[z] = sad4(__ldg(rowPtr(col, vw.pitch, mirrorSearch(bv + candOffset<R>(z), vw.dimV))), f2, acc[z]);
+                        acc[z] = sad4(fetchPixel(vw.y1, vw.c1, vw.pitch, mirrorSearch(bv + candOffset<R>(z), vw.dimV), fu), f2, acc[z]);
                 }
             }
         }
@@ -170,13 +170,13 @@ template <int R> int launchPassR(hrb_ofc* h, const SearchArgs& a, int step, unsi
     const int lu = step == 1 ? a.lw : a.lh, lv = step == 1 ? a.lh : a.lw;  // X steps run on the transposed planes (View)
     const dim3 grid((lu + TILE - 1) / TILE, (lv + TILE - 1) / TILE, 1);
     bool done = false;
-    if (a.rs == 0 && a.ws <= (h->searchVariant == 0 ? 32 : 16) && h->searchVariant != 1) {  // staged small-window kernel (kernels_search_cand.cu)
+    if (a.rs == 0 && a.ws <= 32 && h->searchVariant != 1) {  // staged small-window kernel (kernels_search_cand.cu)
         const int rc = launchSearchPassCand(h, a, R, step);
         if (rc > 0) return rc;
         done = rc == HRB_OK;
     }
-    if (!done && a.rs == 0 && a.ws >= 32 && h->searchVariant != 1) {  // sliding-window kernels (kernels_search_big.cu), finalize fused
-        const int rc = launchSearchPassBig(h, a, R, step);
+    if (!done && a.rs == 0 && a.ws >= 64 && h->searchVariant != 1) {  // sliding-window kernels (kernels_search_slide.cu), finalize fused
+        const int rc = launchSearchPassSlide(h, a, R, step);
         if (rc > 0) return rc;
         if (rc == HRB_OK) {
             *launches = 1;

@@ -87,13 +87,12 @@ __device__ __forceinline__ void candGroups(const SearchArgs& a, const View<STEP>
             if (FULL || t.staged) {
                 // word index of (row cv0 + ov + LO, column cu + ou) inside the staged region
                 const uint32_t* __restrict__ q = &t.s_f1[(cv0 - t.V0 + ov - t.minOv) * SP + (lane + ou - t.minOu + t.sh)];
-                const uint32_t* __restrict__ p2 = rowPtr(vw.p2 + cu, vw.pitch, cv0);
                 constexpr int RB = GH < 8 ? GH : 8;  // frame-2 rows loaded before the first one is consumed
 #pragma unroll
                 for (int r0 = 0; r0 < GH; r0 += RB) {
                     uint32_t f2r[RB];
 #pragma unroll
-                    for (int r = 0; r < RB; ++r) f2r[r] = (FULL || cv0 + r0 + r < vw.lv) ? __ldg(rowPtr(p2, vw.pitch, r0 + r)) : 0u;
+                    for (int r = 0; r < RB; ++r) f2r[r] = (FULL || cv0 + r0 + r < vw.lv) ? fetchPixel(vw.y2, vw.c2, vw.pitch, cv0 + r0 + r, cu) : 0u;
 #pragma unroll
                     for (int r = 0; r < RB; ++r) {
                         if (FULL || cv0 + r0 + r < vw.lv) {
@@ -103,13 +102,13 @@ __device__ __forceinline__ void candGroups(const SearchArgs& a, const View<STEP>
                     }
                 }
             } else {
-                const uint32_t* __restrict__ col = vw.p1 + mirrorSearch(cu + ou, vw.dimU);
+                const int fu = mirrorSearch(cu + ou, vw.dimU);
                 for (int r = 0; r < GH; ++r) {
                     if (cv0 + r >= vw.lv) break;
-                    const uint32_t f2 = __ldg(rowPtr(vw.p2 + cu, vw.pitch, cv0 + r));
+                    const uint32_t f2 = fetchPixel(vw.y2, vw.c2, vw.pitch, cv0 + r, cu);
                     const int bv = cv0 + r + ov;
 #pragma unroll
-                    for (int z = 0; z < R; ++z) acc[z] = sad4(__ldg(rowPtr(col, vw.pitch, mirrorSearch(bv + candOffset<R>(z), vw.dimV))), f2, acc[z]);
+                    for (int z = 0; z < R; ++z) acc[z] = sad4(fetchPixel(vw.y1, vw.c1, vw.pitch, mirrorSearch(bv + candOffset<R>(z), vw.dimV), fu), f2, acc[z]);
                 }
             }
         }
@@ -230,16 +229,35 @@ template <int R, int STEP, bool TAPS, int WS> __global__ void __launch_bounds__(
     if (staged) {
         const bool interior = ca >= 0 && ca + SP <= vw.pitch && cb + RU <= vw.dimU && rb >= 0 && rb + RV <= vw.dimV;
         if (interior) {
+            // the region is assembled from the planes: one luma word and one chroma word give four {Y,U,V,0} words
+            // (expand4); four rows per iteration keep eight loads of a thread in flight
             const int c4 = tid & 15;
             if (c4 < SP / 4) {
-                const uint32_t* __restrict__ src = vw.p1 + ca + c4 * 4;
-                for (int r = tid >> 4; r < RV; r += 16) cpAsync16(&s_f1[r * SP + c4 * 4], rowPtr(src, vw.pitch, rb + r));
+                const uint8_t* __restrict__ ysrc = vw.y1 + ca + c4 * 4;
+                const uint8_t* __restrict__ csrc = vw.c1 + ca + c4 * 4;
+                for (int r = tid >> 4; r < RV; r += 64) {
+                    uint32_t yw[4], cw[4];
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        const int rr = min(r + 16 * i, RV - 1);
+                        yw[i] = __ldg(reinterpret_cast<const uint32_t*>(rowPtr(ysrc, vw.pitch, rb + rr)));
+                        cw[i] = __ldg(reinterpret_cast<const uint32_t*>(rowPtr(csrc, vw.pitch, (rb + rr) >> 1)));
+                    }
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        const int rr = r + 16 * i;
+                        if (rr < RV) {
+                            uint32_t w[4];
+                            expand4(yw[i], cw[i], w);
+                            *reinterpret_cast<uint4*>(&s_f1[rr * SP + c4 * 4]) = make_uint4(w[0], w[1], w[2], w[3]);
+                        }
+                    }
+                }
             }
-            cpAsyncWaitAll();
         } else {
             for (int idx = tid; idx < RV * SP; idx += 256) {
                 const int r = idx / SP, c = idx - r * SP;
-                s_f1[idx] = __ldg(rowPtr(vw.p1 + mirrorSearch(ca + c, vw.dimU), vw.pitch, mirrorSearch(rb + r, vw.dimV)));
+                s_f1[idx] = fetchPixel(vw.y1, vw.c1, vw.pitch, mirrorSearch(rb + r, vw.dimV), mirrorSearch(ca + c, vw.dimU));
             }
         }
     }

@@ -28,19 +28,22 @@ __device__ __forceinline__ uint32_t sad4(uint32_t a, uint32_t b, uint32_t c) {
     return d;
 }
 
-// A pass seen along its candidate axis: v is the axis the candidates move along and the row index of the plane in
-// use, u the contiguous axis (one lane per u).  Y steps read the row-major search planes (u = x, v = y); X steps read
-// the TRANSPOSED planes (u = y, v = x).  Both steps therefore run the same code and every warp access is a
-// contiguous row segment.  Window bookkeeping (offset arrays, biases) stays in (x, y).
+// A pass seen along its candidate axis: v is the axis the candidates move along and the row index of the planes in
+// use, u the contiguous axis.  Y steps read the row-major planes (u = x, v = y); X steps read the TRANSPOSED planes
+// (u = y, v = x).  Both steps therefore run the same code and every warp access is a contiguous row segment.  In
+// either orientation the chroma bytes that belong to luma sample (v, u) are c[(v >> 1) * pitch + (u & ~1)] and + 1
+// (hrb_internal.cuh, SearchArgs).  Window bookkeeping (offset arrays, biases) stays in (x, y).
 template <int STEP> struct View {
-    const uint32_t* __restrict__ p1;
-    const uint32_t* __restrict__ p2;
+    const uint8_t* __restrict__ y1;
+    const uint8_t* __restrict__ c1;
+    const uint8_t* __restrict__ y2;
+    const uint8_t* __restrict__ c2;
     int pitch, dimU, dimV, lu, lv;
     __device__ __forceinline__ explicit View(const SearchArgs& a) {
         if (STEP == 1) {
-            p1 = a.plane1; p2 = a.plane2; pitch = a.pitch; dimU = a.W; dimV = a.H; lu = a.lw; lv = a.lh;
+            y1 = a.y1; c1 = a.c1; y2 = a.y2; c2 = a.c2; pitch = a.pitch; dimU = a.W; dimV = a.H; lu = a.lw; lv = a.lh;
         } else {
-            p1 = a.planeT1; p2 = a.planeT2; pitch = a.pitchT; dimU = a.H; dimV = a.W; lu = a.lh; lv = a.lw;
+            y1 = a.yT1; c1 = a.cT1; y2 = a.yT2; c2 = a.cT2; pitch = a.pitchT; dimU = a.H; dimV = a.W; lu = a.lh; lv = a.lw;
         }
     }
     static __device__ __forceinline__ int wx(int wu, int wv) { return STEP == 1 ? wu : wv; }
@@ -49,12 +52,31 @@ template <int STEP> struct View {
     static __device__ __forceinline__ int ov(int ox, int oy) { return STEP == 1 ? oy : ox; }
 };
 
-// base + rows * pitch (in words) as ONE IMAD.WIDE on the FMA pipe: keeps the per-fetch address arithmetic off the
+// base + rows * pitch (bytes) as ONE IMAD.WIDE on the FMA pipe: keeps the per-fetch address arithmetic off the
 // ALU pipe, which the VABSDIFF4 stream saturates (nvcc otherwise emits 4-5 ALU instructions per row-strided fetch).
-__device__ __forceinline__ const uint32_t* rowPtr(const uint32_t* base, int pitchWords, int rows) {
+__device__ __forceinline__ const uint8_t* rowPtr(const uint8_t* base, int pitchBytes, int rows) {
     unsigned long long r;
-    asm("mad.wide.s32 %0, %1, %2, %3;" : "=l"(r) : "r"(pitchWords), "r"(rows * 4), "l"((unsigned long long)base));
-    return reinterpret_cast<const uint32_t*>(r);
+    asm("mad.wide.s32 %0, %1, %2, %3;" : "=l"(r) : "r"(pitchBytes), "r"(rows), "l"((unsigned long long)base));
+    return reinterpret_cast<const uint8_t*>(r);
+}
+
+// The reference's three samples of one pixel as a word {Y, U, V, 0}: one VABSDIFF4 on two such words is its 3-term
+// delta (calcDeltaSumsKernelSDR.h:98-100).  (v, u) must be inside the frame.
+__device__ __forceinline__ uint32_t fetchPixel(const uint8_t* __restrict__ y, const uint8_t* __restrict__ c, int pitch, int v, int u) {
+    const uint32_t l = __ldg(rowPtr(y, pitch, v) + u);
+    const uint32_t uv = __ldg(reinterpret_cast<const uint16_t*>(rowPtr(c, pitch, v >> 1) + (u & ~1)));
+    return l | (uv << 8);
+}
+
+// Four horizontally adjacent pixels (u0 a multiple of 4) as four {Y, U, V, 0} words, from one luma word and one
+// chroma word: 6 PRMT.
+__device__ __forceinline__ void expand4(uint32_t yw, uint32_t cw, uint32_t (&w)[4]) {
+    const uint32_t cA = __byte_perm(cw, 0u, 0x4104);  // {0, U0, V0, 0}
+    const uint32_t cB = __byte_perm(cw, 0u, 0x4324);  // {0, U1, V1, 0}
+    w[0] = __byte_perm(yw, cA, 0x7650);
+    w[1] = __byte_perm(yw, cA, 0x7651);
+    w[2] = __byte_perm(yw, cB, 0x7652);
+    w[3] = __byte_perm(yw, cB, 0x7653);
 }
 
 // 16-byte asynchronous copy global -> shared (LDGSTS): no register staging, so a thread keeps all its copies in
