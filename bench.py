@@ -515,12 +515,18 @@ def main():
     calc.m_opticalFlowSearchRadius = args.radius
 
     # synthetic frames: a ring of distinct frames, device-resident and pinned-host copies
-    RING = 6
+    # ring of distinct frames played back and forth (0 1 2 3 4 5 4 3 2 1 0 1 ...): every consecutive pair is one step of
+    # the scene's motion, forward or backward — a wrap from the last frame to the first would be a scene cut every 6 frames
+    NFR = 6
+    PING = list(range(NFR)) + list(range(NFR - 2, 0, -1))
+    RING = len(PING)
     dt_np = np.uint16 if hdr else np.uint8
-    host_frames = [synth.make_frame(W, H, t, synth.SEED_BASE + 2 + rank, hdr) for t in range(RING)]
+    distinct = [synth.make_frame(W, H, t, synth.SEED_BASE + 2 + rank, hdr) for t in range(NFR)]
     tdt = torch.int16 if hdr else torch.uint8
-    pinned = [torch.from_numpy(f.view(np.int16) if hdr else f).pin_memory() for f in host_frames]
-    dev = [p.cuda(non_blocking=False) for p in pinned]
+    pinned_d = [torch.from_numpy(f.view(np.int16) if hdr else f).pin_memory() for f in distinct]
+    dev_d = [p.cuda(non_blocking=False) for p in pinned_d]
+    pinned = [pinned_d[t] for t in PING]
+    dev = [dev_d[t] for t in PING]
     out_pinned = torch.empty(calc.outputFrameBytes // (2 if hdr else 1), dtype=tdt).pin_memory()
     torch.cuda.synchronize()
 

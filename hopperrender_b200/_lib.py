@@ -81,6 +81,8 @@ PROTOTYPES = {
     "hrb_ofc_set_search_variant": (C.c_int, [_P, C.c_int]),
     "hrb_ofc_set_flow_overlap": (C.c_int, [_P, C.c_int]),
     "hrb_ofc_join_flow": (C.c_int, [_P]),
+    "hrb_ofc_debug_timeline": (C.c_int, [_P, C.c_size_t]),
+    "hrb_ofc_debug_timeline_read": (C.c_int, [_P, C.c_void_p, C.c_size_t]),
     "hrb_kernel_launch_count": (C.c_uint64, []),
     "hrb_microbench_sad_peak": (C.c_int, [C.c_int, C.POINTER(C.c_double)]),
     "hrb_last_error": (C.c_char_p, []),

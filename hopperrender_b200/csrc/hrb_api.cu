@@ -175,6 +175,7 @@ static int issueFlowKernels(hrb_ofc* h, int R, int ws0, int iterations, bool iss
             a.rawDelta = (iter == 0 && step == 0) ? h->rawDeltaDev : nullptr;
             a.tapSums = nullptr;
             a.tapLayer = nullptr;
+            a.dbg = h->dbgDev ? h->dbgDev + (size_t)(iter * 2 + step) * h->dbgStride : nullptr;
             if (h->tapMode) {
                 PassTapDev t;
                 t.g.windowSize = ws;
@@ -248,7 +249,7 @@ static void dropFlowGraphs(hrb_ofc* h) {
 // Launches the flow kernels through a CUDA graph captured on first use for this combination of buffers and parameters
 // (24 dependent launches at 4K become one); falls back to plain launches whenever capture is not possible.
 static int launchFlowKernels(hrb_ofc* h, int R, int ws0, int iterations) {
-    if (!h->flowGraphsOn || h->tapMode || h->prof.on) return issueFlowKernels(h, R, ws0, iterations, true);
+    if (!h->flowGraphsOn || h->tapMode || h->prof.on || h->dbgDev) return issueFlowKernels(h, R, ws0, iterations, true);
     hrb_ofc::FlowGraph key;
     key.plane1 = h->searchPlane[1].base;
     key.plane2 = h->searchPlane[2].base;
@@ -678,6 +679,7 @@ void hrb_ofc_destroy(hrb_ofc* h) {
     if (h->spareFreeEvent) cudaEventDestroy(h->spareFreeEvent);
     dropFlowGraphs(h);
     freeTmaCache(h);
+    cudaFree(h->dbgDev);
     if (h->upStream) cudaStreamDestroy(h->upStream);
     if (h->flowStream) cudaStreamDestroy(h->flowStream);
     if (h->flowForkEvent) cudaEventDestroy(h->flowForkEvent);
@@ -1091,6 +1093,30 @@ int hrb_ofc_set_search_variant(hrb_ofc* h, int variant) {
     HRB_REQUIRE(variant >= 0 && variant <= 3, "variant must be 0 (automatic), 1 (generic kernels only), 2 (sliding kernel staged without TMA) or 3 (sliding kernel without the aligned fast path)");
     h->searchVariant = variant;
     h->warpVariant = variant == 1 ? 1 : 0;
+    return HRB_OK;
+}
+
+// Debug aid: per-CTA timelines of the tile search kernels (8 words per CTA: start, boxes landed, runs done, end
+// [globaltimer ns], SM id, block x, block y, rounds), `words_per_pass` words for each of up to 32 passes.
+int hrb_ofc_debug_timeline(hrb_ofc* h, size_t words_per_pass) {
+    HRB_REQUIRE(h, "null handle");
+    HRB_CUDA(cudaSetDevice(h->device));
+    HRB_CUDA(cudaStreamSynchronize(h->stream));
+    cudaFree(h->dbgDev);
+    h->dbgDev = nullptr;
+    h->dbgStride = words_per_pass;
+    if (words_per_pass) {
+        HRB_CUDA(cudaMalloc(&h->dbgDev, words_per_pass * 32 * sizeof(unsigned long long)));
+        HRB_CUDA(cudaMemset(h->dbgDev, 0, words_per_pass * 32 * sizeof(unsigned long long)));
+    }
+    return HRB_OK;
+}
+int hrb_ofc_debug_timeline_read(hrb_ofc* h, void* dst, size_t bytes) {
+    HRB_REQUIRE(h && dst && h->dbgDev, "no timeline buffer");
+    HRB_REQUIRE(bytes <= h->dbgStride * 32 * sizeof(unsigned long long), "size larger than the buffer");
+    HRB_CUDA(cudaSetDevice(h->device));
+    HRB_CUDA(cudaDeviceSynchronize());
+    HRB_CUDA(cudaMemcpy(dst, h->dbgDev, bytes, cudaMemcpyDeviceToHost));
     return HRB_OK;
 }
 

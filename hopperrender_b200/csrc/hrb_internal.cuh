@@ -76,6 +76,7 @@ struct SearchArgs {
     uint32_t* rawDelta;    // non-null in pass 0: receives sums[R/2-1][window 0]
     uint32_t* tapSums;     // optional [R][nWy][nWx]
     uint8_t* tapLayer;     // optional [nWy][nWx]
+    unsigned long long* dbg;  // optional per-CTA timeline of this pass (hrb_ofc_debug_timeline): 8 words per CTA
 };
 
 // The search representation of one input slot: 8-bit planes in both orientations, one allocation.
@@ -197,6 +198,8 @@ struct hrb_ofc {
     std::vector<hrb::PassTapDev> taps;
     hrb::Profile prof;
     hrb::TmaCache* tmaCache = nullptr;  // TMA descriptors of the search planes, encoded on first use
+    unsigned long long* dbgDev = nullptr;  // per-CTA timelines of the search passes (debug aid, off by default)
+    size_t dbgStride = 0;                  // words per pass
 };
 
 namespace hrb {

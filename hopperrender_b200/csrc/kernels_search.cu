@@ -170,18 +170,15 @@ template <int R> int launchPassR(hrb_ofc* h, const SearchArgs& a, int step, unsi
     const int lu = step == 1 ? a.lw : a.lh, lv = step == 1 ? a.lh : a.lw;  // X steps run on the transposed planes (View)
     const dim3 grid((lu + TILE - 1) / TILE, (lv + TILE - 1) / TILE, 1);
     bool done = false;
-    if (a.rs == 0 && a.ws <= 32 && h->searchVariant != 1) {  // staged small-window kernel (kernels_search_cand.cu)
-        const int rc = launchSearchPassCand(h, a, R, step);
+    if (a.rs == 0 && a.ws >= 4 && h->searchVariant != 1) {  // tile kernels on the planar planes (kernels_search_slide.cu), finalize fused
+        const int rc = launchSearchPassSlide(h, a, R, step);
         if (rc > 0) return rc;
         done = rc == HRB_OK;
     }
-    if (!done && a.rs == 0 && a.ws >= 64 && h->searchVariant != 1) {  // sliding-window kernels (kernels_search_slide.cu), finalize fused
-        const int rc = launchSearchPassSlide(h, a, R, step);
+    if (!done && a.rs == 0 && a.ws <= 32 && h->searchVariant != 1) {  // staged small-window kernel (kernels_search_cand.cu): 2x2 windows
+        const int rc = launchSearchPassCand(h, a, R, step);
         if (rc > 0) return rc;
-        if (rc == HRB_OK) {
-            *launches = 1;
-            return HRB_OK;
-        }
+        done = rc == HRB_OK;
     }
     if (!done) {
         // generic kernel; windows larger than its tile are finalized by the last CTA of each window

@@ -1,28 +1,32 @@
-// kernels_search_slide.cu — search passes for windows of 64x64 flow pixels and larger at full flow resolution
-// (12 of the 22 passes at 4K).  Same arithmetic as sadPassKernel (kernels_search.cu), different data movement.
+// kernels_search_slide.cu — search passes for windows of 4x4 flow pixels and larger at full flow resolution
+// (20 of the 22 passes at 4K).  Same arithmetic as sadPassKernel (kernels_search.cu), different data movement.
 //
 // Data: the 8-bit planar search planes (luma + NV12-style chroma, see SearchArgs), so one VABSDIFF4 covers FOUR
-// luma pixels, or the U,V samples of four pixels, instead of one pixel: half the SAD instructions of a {Y,U,V,0}
-// word per pixel, and the two frames of a pass are 25 MB — they stay in the 126 MB L2 over the whole ladder.
+// luma pixels, or the U,V samples of four pixels, instead of one pixel, and the two frames of a pass are 25 MB —
+// they stay in the 126 MB L2 over the whole ladder.
 //
 // Work split (u = contiguous axis, v = candidate axis, see View): a CTA owns a tile of 128 (u) x 32*NWV (v) flow
-// pixels inside ONE window row; a warp owns 128 x 32 of it, a lane a column of 4 pixels (one word) x 32 rows.
-//   * frame 1: the (32*NWV + HI-LO) luma rows and the matching chroma rows every candidate of the tile can touch
-//     are staged in shared memory by TMA (cp.async.bulk.tensor.2d, one elected thread, completion on an mbarrier);
-//     the box starts at the 16-byte boundary below the window's displaced column (TMA needs that alignment), each
-//     lane then re-aligns its words with one funnel shift per sample (skipped when the displacement is a multiple
-//     of 4).  Boxes that leave the frame come back zero-filled there; the CTA patches those bytes through the
-//     reference's mirror (calcDeltaSumsKernelSDR.h:86-95).
-//   * along v every lane slides over the staged column: each frame-1 sample is fetched ONCE and feeds every
+// pixels; a warp owns 128 x 32 of it, a lane a column of 4 pixels (one word), which it walks in runs of
+// RUN = min(ws, 32) rows (one window row per run).
+//   * frame 1: ONE luma box and ONE chroma box per tile hold every sample any candidate of any window of the tile can
+//     touch: tile + candidate span + the spread of the tile's window displacements (motion fields are smooth: a few
+//     pixels).  They are staged by TMA (cp.async.bulk.tensor.2d issued by one elected thread, completion on an
+//     mbarrier); the box starts at the 16-byte boundary below the smallest displaced column (TMA needs that
+//     alignment), each lane re-aligns its words with one funnel shift per sample.  Boxes that leave the frame come
+//     back zero-filled there; the CTA patches those bytes through the reference's mirror
+//     (calcDeltaSumsKernelSDR.h:86-95).  Tiles whose displacements spread beyond the box take a per-pixel path.
+//   * along v every lane slides over its staged column: each frame-1 sample is fetched ONCE and feeds every
 //     (row, candidate) pair it belongs to (up to R of them), all register indices being compile-time.
 //   * chroma: the U,V pair of luma (v, u) is c[v >> 1][u & ~1].  Along v, luma rows 2k and 2k+1 with displacement s
 //     read chroma rows k + ((e + s) >> 1), e = 0, 1: the same row when s is even (one SAD, weight 2), two rows when
 //     it is odd.  Along u, a displacement ou maps a pixel pair onto one chroma pair when ou is even (weight 2) and
-//     onto two neighbouring pairs when it is odd (two staged boxes, ou - 1 and ou + 1, weight 1 each).
-//   * the warp reduces its R sums with a recursive-halving butterfly, adds them to the per-window scratch and the
-//     last contributor of a window (arrival ticket) finalizes it: arg-min + offset update, no extra launch.
+//     onto two neighbouring pairs when it is odd (two passes over the staged rows, 2 bytes apart, weight 1 each).
+//   * windows up to 32 pixels are reduced and finalized inside the warp (butterfly over the window's lanes), 64-pixel
+//     windows inside the CTA, larger ones through R atomics per CTA into the per-window scratch: the last CTA of a
+//     window (arrival ticket) finalizes it.  No fills, no extra launch.
 #include <cuda.h>
 
+#include <climits>
 #include <cstring>
 #include <mutex>
 
@@ -40,17 +44,29 @@ template <int R> struct CandSpan {
 
 __host__ __device__ constexpr int floorHalf(int v) { return v >= 0 ? (v >> 1) : -((1 - v) >> 1); }
 __host__ __device__ constexpr int align128(int v) { return (v + 127) & ~127; }
+__host__ __device__ constexpr int ilog2c(int v) { return v <= 1 ? 0 : 1 + ilog2c(v >> 1); }
 
-// geometry of the staged boxes of one window column of a tile
-template <int R, int NWV, int NWIN> struct SlideGeom {
-    static constexpr int SEGW = 128 / NWIN;                              // pixels (bytes) of a window column inside the tile
-    static constexpr int BW = SEGW + 16;                                 // box width: 16-byte aligned superset
-    static constexpr int BWW = BW / 4;                                   // ... in words
-    static constexpr int ROWS = 32 * NWV + CandSpan<R>::SPAN;            // luma rows
-    static constexpr int ROWSC = (32 * NWV + CandSpan<R>::SPAN) / 2 + 2; // chroma rows
-    static constexpr int LUMA_BYTES = align128(ROWS * BW);
-    static constexpr int CHROMA_BYTES = align128(ROWSC * BW);
-    static constexpr int SMEM = NWIN * (LUMA_BYTES + CHROMA_BYTES) + 128;  // + slack to align the base to 128 bytes
+// window-size class WSC: 4, 8, 16, 32, 64 or 128 (= every window of 128 pixels and more)
+template <int WSC> struct Cls {
+    static constexpr int RUN = WSC < 32 ? WSC : 32;          // rows of one run (one window row)
+    static constexpr int NRUN = 32 / RUN;                    // runs of a warp
+    static constexpr int SEG = (WSC < 128 ? WSC : 128) / 4;  // lanes per window
+    static constexpr bool SPREAD = WSC < 128;                // the windows of a tile may be displaced differently
+    static constexpr int SU = SPREAD ? 12 : 0;               // displacement spread the boxes cover, along u ...
+    static constexpr int SV = SPREAD ? 15 : 0;               // ... and along v
+    static constexpr int BW = SPREAD ? 160 : 144;            // box width in bytes: 128 + 16-byte alignment slack + spread
+    static constexpr int BWW = BW / 4;
+};
+
+// Launch-time geometry (host and device agree through this struct).
+struct TileParams {
+    int nwv;          // warps of a CTA = tile rows / 32
+    int rowsY;        // luma rows of the staged box (cp.async, 16 bytes per copy)
+    int boxHC;        // chroma rows of the staged box (one TMA box)
+    int lumaBytes;    // shared-memory bytes of the luma rows (multiple of 128)
+    int chromaBytes;
+    int useTma;       // 0: stage with plain loads (A/B, and when no tensor map could be encoded)
+    int forceSlow;    // 1: every tile takes the per-pixel path (A/B and parity coverage of that path)
 };
 
 // ---- mbarrier / TMA -------------------------------------------------------------------------------------------
@@ -82,16 +98,23 @@ __device__ __forceinline__ void tmaLoad2d(void* dst, const CUtensorMap* map, int
 
 // ---- the sliding loops ---------------------------------------------------------------------------------------------
 // luma: acc[z] += sum over the run's rows p of SAD4(frame1 row p + d_z, frame2 row p); fetch(j) returns the lane's
-// frame-1 word of staged row j = p + d_z - LO.
-template <int R, typename Fetch> __device__ __forceinline__ void slideLuma(uint32_t (&acc)[16], const uint32_t (&f2)[32], Fetch fetch) {
+// frame-1 word of staged row j = p + d_z - LO.  Samples no (row, candidate) pair uses are never fetched.
+template <int R, int RUN, typename Fetch> __device__ __forceinline__ void slideLuma(uint32_t (&acc)[16], const uint32_t (&f2)[RUN], Fetch fetch) {
     constexpr int LO = CandSpan<R>::LO;
 #pragma unroll
-    for (int j = 0; j < 32 + CandSpan<R>::SPAN; ++j) {
+    for (int j = 0; j < RUN + CandSpan<R>::SPAN; ++j) {
+        bool used = false;
+#pragma unroll
+        for (int z = 0; z < R; ++z) {
+            const int p = j - (candOffset<R>(z) - LO);
+            used = used || (p >= 0 && p < RUN);
+        }
+        if (!used) continue;
         const uint32_t f1 = fetch(j);
 #pragma unroll
         for (int z = 0; z < R; ++z) {
             const int p = j - (candOffset<R>(z) - LO);
-            if (p >= 0 && p < 32) acc[z] = sad4(f1, f2[p], acc[z]);
+            if (p >= 0 && p < RUN) acc[z] = sad4(f1, f2[p], acc[z]);
         }
     }
 }
@@ -99,371 +122,547 @@ template <int R, typename Fetch> __device__ __forceinline__ void slideLuma(uint3
 // chroma: PI = parity of the window's displacement along v.  Luma rows 2k + e of the run with candidate z read
 // staged chroma row k + floorHalf(e + PI + d_z) - AMIN; e = 0 and e = 1 coincide when PI + d_z is even (one SAD,
 // the caller doubles the sum, chromaShift).
-template <int R, int PI, typename Fetch> __device__ __forceinline__ void slideChroma(uint32_t (&acc)[16], const uint32_t (&f2c)[16], Fetch fetch) {
+template <int R, int RUN, int PI, typename Fetch> __device__ __forceinline__ void slideChroma(uint32_t (&acc)[16], const uint32_t (&f2c)[RUN / 2], Fetch fetch) {
     constexpr int LO = CandSpan<R>::LO, HI = CandSpan<R>::HI;
     constexpr int AMIN = floorHalf(PI + LO);
-    constexpr int CLEN = 16 + floorHalf(1 + PI + HI) - AMIN;
+    constexpr int CLEN = RUN / 2 + floorHalf(1 + PI + HI) - AMIN;
 #pragma unroll
     for (int jc = 0; jc < CLEN; ++jc) {
+        bool used = false;
+#pragma unroll
+        for (int z = 0; z < R; ++z) {
+            const int k0 = jc - (floorHalf(PI + candOffset<R>(z)) - AMIN), k1 = jc - (floorHalf(1 + PI + candOffset<R>(z)) - AMIN);
+            used = used || (k0 >= 0 && k0 < RUN / 2) || (k1 >= 0 && k1 < RUN / 2);
+        }
+        if (!used) continue;
         const uint32_t c1 = fetch(jc);
 #pragma unroll
         for (int z = 0; z < R; ++z) {
             const int a0 = floorHalf(PI + candOffset<R>(z)) - AMIN;
             const int a1 = floorHalf(1 + PI + candOffset<R>(z)) - AMIN;
             const int k0 = jc - a0, k1 = jc - a1;
-            if (k0 >= 0 && k0 < 16) acc[z] = sad4(c1, f2c[k0], acc[z]);
-            if (a1 != a0 && k1 >= 0 && k1 < 16) acc[z] = sad4(c1, f2c[k1], acc[z]);
+            if (k0 >= 0 && k0 < RUN / 2) acc[z] = sad4(c1, f2c[k0], acc[z]);
+            if (a1 != a0 && k1 >= 0 && k1 < RUN / 2) acc[z] = sad4(c1, f2c[k1], acc[z]);
         }
     }
 }
-template <int R, int PI> __device__ __forceinline__ int chromaShift(int z) { return ((PI + candOffset<R>(z)) & 1) ? 0 : 1; }
+template <int R> __device__ __forceinline__ int chromaShift(int pi, int z) { return ((pi + candOffset<R>(z)) & 1) ? 0 : 1; }
 
-// Patches the bytes of a staged box that lie outside the plane (TMA zero-fills them) with the reference's mirrored
-// samples; `all` stages every byte this way (no TMA).  PAIRS: chroma plane — columns are mirrored as (U,V) pairs.
-// Box row r / byte c <-> plane row rb + r / byte ca + c; only rows [0, rows) and bytes [c0, c1) are ever read.
-template <bool PAIRS>
-__device__ __forceinline__ void patchBox(uint8_t* __restrict__ buf, int bw, const uint8_t* __restrict__ plane, int pitch, int dimU, int dimV, int rb, int ca, int rows,
-                                         int c0, int c1, bool all, int tid, int nThreads) {
-    const int cols = c1 - c0;
-    auto fix = [&](int r, int c) {
-        const int vr = mirrorSearch(rb + r, dimV);
-        const int vcRaw = ca + c;
-        int vc;
-        if (PAIRS)
-            vc = 2 * mirrorSearch(vcRaw >> 1, dimU >> 1) + (vcRaw & 1);
-        else
-            vc = mirrorSearch(vcRaw, dimU);
-        buf[r * bw + c] = __ldg(rowPtr(plane, pitch, vr) + vc);
-    };
-    if (all) {
-        for (int i = tid; i < rows * cols; i += nThreads) {
-            const int r = i / cols;
-            fix(r, c0 + (i - r * cols));
-        }
-        return;
+// Staging of a box through the reference's mirror (calcDeltaSumsKernelSDR.h:86-95) without TMA: rows [0, rows) x
+// bytes [c0, c1) of the box; box row r / byte c <-> plane row rb + r / byte ca + c (ca a multiple of 16).  Used for
+// tiles at the frame border and when TMA is off.  PAIRS: chroma plane — columns are mirrored as (U,V) pairs.
+// Every 16-byte chunk is a cp.async copy — all copies of a thread in flight at once, no dependent global load, which
+// would queue behind the staging traffic of the whole grid: rows through the mirrored row index, chunks left / right
+// of the plane from their mirror chunk, which arrives in forward order and is reversed in shared memory afterwards
+// (MirrorBox::fixup, after cpAsyncWaitAll() + a barrier).  Chunks that have no mirror chunk (plane width not a
+// multiple of 16, displacements beyond the frame size) are filled byte by byte in fixup.
+template <bool PAIRS> struct MirrorBox {
+    uint8_t* __restrict__ buf;
+    const uint8_t* __restrict__ plane;
+    int bw, pitch, dimU, dimV, rb, rows, kLo, nK, nCh, pc0;
+    bool whole;
+    __device__ __forceinline__ MirrorBox(uint8_t* buf_, int bw_, const uint8_t* plane_, int pitch_, int dimU_, int dimV_, int rb_, int ca, int rows_, int c0, int c1)
+        : buf(buf_), plane(plane_), bw(bw_), pitch(pitch_), dimU(dimU_), dimV(dimV_), rb(rb_), rows(rows_) {
+        kLo = c0 >> 4;
+        nK = ((c1 + 15) >> 4) - kLo;
+        nCh = dimU >> 4;           // whole chunks of a plane row
+        pc0 = (ca >> 4) + kLo;     // plane chunk of box chunk kLo
+        whole = (dimU & 15) == 0;
     }
-    const int rTop = min(max(-rb, 0), rows);            // rows [0, rTop) lie above the plane
-    const int rBot = min(max(dimV - rb, 0), rows);      // rows [rBot, rows) lie below it
-    const int nOutRows = rTop + (rows - rBot);
-    for (int i = tid; i < nOutRows * cols; i += nThreads) {
-        int r = i / cols;
-        const int c = c0 + (i - r * cols);
-        if (r >= rTop) r += rBot - rTop;
-        fix(r, c);
+    __device__ __forceinline__ int srcChunk(int pc) const { return pc < 0 ? -pc - 1 : (pc >= nCh ? 2 * nCh - pc - 1 : pc); }
+    __device__ __forceinline__ bool direct(int pc) const {  // the chunk is a (possibly reversed) copy of a plane chunk
+        const int sc = srcChunk(pc);
+        return whole ? (sc >= 0 && sc < nCh) : (pc >= 0 && pc < nCh);
     }
-    const int cLeft = min(max(-ca, c0), c1);            // bytes [c0, cLeft) lie left of the plane
-    const int cRight = min(max(dimU - ca, c0), c1);     // bytes [cRight, c1) lie right of it
-    const int nOutCols = (cLeft - c0) + (c1 - cRight);
-    const int nInRows = rBot - rTop;
-    if (nOutCols > 0 && nInRows > 0) {
-        for (int i = tid; i < nInRows * nOutCols; i += nThreads) {
-            const int r = rTop + i / nOutCols;
-            int c = c0 + (i % nOutCols);
-            if (c >= cLeft) c += cRight - cLeft;
-            fix(r, c);
+    __device__ __forceinline__ void issue(int tid, int nThreads) const {
+#pragma unroll 1
+        for (int i = tid; i < rows * nK; i += nThreads) {
+            const int r = i / nK, k = i - r * nK;
+            const int pc = pc0 + k;
+            if (direct(pc)) cpAsync16(buf + r * bw + 16 * (kLo + k), rowPtr(plane, pitch, mirrorSearch(rb + r, dimV)) + 16 * srcChunk(pc));
         }
     }
-}
-
-struct SlideFlags {
-    int useTma;       // 0: stage every box with plain loads (A/B, and when no tensor map could be encoded)
-    int forceFunnel;  // 1: always take the funnel-shift fetch (A/B of the aligned fast path)
+    __device__ __forceinline__ void fixup(int tid, int nThreads) const {
+        const int nLeft = min(max(-pc0, 0), nK);             // box chunks [0, nLeft) lie left of the plane
+        const int rightStart = min(max(nCh - pc0, 0), nK);   // box chunks [rightStart, nK) lie right of it (or straddle its last column)
+        const int nOut = nLeft + (nK - rightStart);
+#pragma unroll 1
+        for (int i = tid; i < rows * nOut; i += nThreads) {
+            const int r = i / nOut;
+            int k = i - r * nOut;
+            if (k >= nLeft) k += rightStart - nLeft;
+            const int pc = pc0 + k;
+            uint8_t* __restrict__ d = buf + r * bw + 16 * (kLo + k);
+            if (direct(pc)) {
+                const uint4 w = *reinterpret_cast<const uint4*>(d);
+                const unsigned sel = PAIRS ? 0x1032u : 0x0123u;  // reverse the (U,V) pairs / the bytes of a word
+                *reinterpret_cast<uint4*>(d) = make_uint4(__byte_perm(w.w, 0u, sel), __byte_perm(w.z, 0u, sel), __byte_perm(w.y, 0u, sel), __byte_perm(w.x, 0u, sel));
+            } else {
+                const uint8_t* __restrict__ srcRow = rowPtr(plane, pitch, mirrorSearch(rb + r, dimV));
+#pragma unroll 1
+                for (int j = 0; j < 16; ++j) {
+                    const int vc = 16 * pc + j;
+                    d[j] = __ldg(srcRow + (PAIRS ? 2 * mirrorSearch(vc >> 1, dimU >> 1) + (vc & 1) : mirrorSearch(vc, dimU)));
+                }
+            }
+        }
+    }
 };
 
+// lean per-layer total: same arithmetic as windowTotal (search_common.cuh), candidate offset given
+__device__ __forceinline__ uint32_t layerTotalOf(const SearchArgs& a, const WindowCtx& c, uint32_t sad, int sq) {
+    const int cand = (int)(short)(c.o + sq);
+    uint32_t bias = (uint32_t)abs(cand);
+    if (c.useNb) bias += __sad(c.nb[0], cand, __sad(c.nb[1], cand, __sad(c.nb[2], cand, __sad(c.nb[3], cand, 0u)))) << a.neighborBiasScalar;
+    return (sad << a.deltaScalar) + c.nw * bias;
+}
+
 // ---- the kernel ------------------------------------------------------------------------------------------------------
-// NWV warps stacked along v, NWIN window columns inside the 128-pixel tile (1: ws >= 128, 2: ws == 64).
-template <int R, int STEP, int NWV, int NWIN>
-__global__ void __launch_bounds__(32 * NWV, NWIN == 1 ? 4 : 5)
-    sadSlidePlanarKernel(const SearchArgs a, const __grid_constant__ CUtensorMap mapY, const __grid_constant__ CUtensorMap mapC, const SlideFlags flags) {
-    using G = SlideGeom<R, NWV, NWIN>;
+// Windows of a tile whose displacements do not fit one pair of boxes are handled in ROUNDS: each round picks the
+// pending windows around the smallest pending displacement, stages their boxes and runs them; a smooth field needs
+// one round, a tile on a motion boundary two or three.  What is left after MAX_ROUNDS takes the per-pixel path.
+constexpr int MAX_ROUNDS = 4;
+
+template <int R, int STEP, int WSC>
+__global__ void __maxnreg__(128)
+    sadTileKernel(const SearchArgs a, const __grid_constant__ CUtensorMap mapC, const TileParams tp) {
+    using C = Cls<WSC>;
     constexpr int LO = CandSpan<R>::LO, SPAN = CandSpan<R>::SPAN;
-    constexpr int NT = 32 * NWV;
+    constexpr int RUN = C::RUN, BW = C::BW, BWW = C::BWW;
+    constexpr int WSL = WSC < 128 ? ilog2c(WSC) : 0;  // log2 of the window size for the classes below 128
     extern __shared__ uint8_t smemRaw[];
     __shared__ uint64_t barY, barC;
+    __shared__ int s_rng[4];           // min ou, max ou, min ov, max ov over the windows of the current round
+    __shared__ uint32_t s_red[8][16];  // CTA-level sums: [window of the tile][layer] (classes 64 and 128)
     uint8_t* const smem = smemRaw + ((128u - ((unsigned)__cvta_generic_to_shared(smemRaw) & 127u)) & 127u);
-    auto bufY = [&](int win) { return smem + win * G::LUMA_BYTES; };
-    auto bufC = [&](int win) { return smem + NWIN * G::LUMA_BYTES + win * G::CHROMA_BYTES; };
+    uint8_t* const bufY = smem;
+    uint8_t* const bufC = smem + tp.lumaBytes;
+    int* const s_off = reinterpret_cast<int*>(smem + tp.lumaBytes + tp.chromaBytes);  // per window of the tile: (ou & 0xffff) | (ov << 16)
+    const int TV = 32 * tp.nwv;
+    const int nwu = C::SPREAD ? (128 >> WSL) : 1;        // windows of the tile along u, v
+    const int nwv = C::SPREAD ? (TV >> WSL) : 1;
+    uint8_t* const s_state = reinterpret_cast<uint8_t*>(s_off + nwu * nwv);  // 0 pending, 1 in this round, 2 done / not there
 
     const View<STEP> vw(a);
     const int lane = threadIdx.x, warp = threadIdx.y;
+    const int NT = 32 * tp.nwv;
     const int tid = warp * 32 + lane;
-    const int U0 = blockIdx.x * 128, V0 = blockIdx.y * 32 * NWV;
-    const int wv = V0 >> a.wsLog2;
-    const int rowsLeft = vw.lv - V0;                                  // > 0 by the grid
-    const int rowsNeeded = min(G::ROWS, rowsLeft + SPAN);            // luma rows of the boxes that are ever read
+    const int U0 = blockIdx.x * 128, V0 = blockIdx.y * TV;
+    const int wsLog2 = WSC < 128 ? WSL : a.wsLog2;
+    const int tileRows = min(TV, vw.lv - V0);            // flow rows of the tile that exist (> 0 by the grid)
+    const int tileCols = min(128, vw.lu - U0);           // ... columns (a multiple of 4)
 
-    // per window column of the tile: displacement, box origins, border flags (every thread computes both: cheap, uniform)
-    int ouW[NWIN], ovW[NWIN];
-    bool existW[NWIN];
-    bool anyOdd = false, border = false;
-#pragma unroll
-    for (int w = 0; w < NWIN; ++w) {
-        const int uw = U0 + w * G::SEGW;
-        existW[w] = uw < vw.lu;
-        ouW[w] = ovW[w] = 0;
-        if (existW[w]) {
-            const int wu = uw >> a.wsLog2;
-            int ox, oy;
-            loadWindowOffsets<STEP>(a, View<STEP>::wx(wu, wv), View<STEP>::wy(wu, wv), ox, oy);
-            ouW[w] = View<STEP>::ou(ox, oy);
-            ovW[w] = View<STEP>::ov(ox, oy);
-            anyOdd |= (ouW[w] & 1) != 0;
-            const int segValid = min(G::SEGW, vw.lu - uw);
-            const int cb = uw + ouW[w], rb = V0 + ovW[w] + LO;
-            border |= cb < 0 || cb + segValid + 2 > vw.dimU || rb < 0 || rb + rowsNeeded > vw.dimV;  // + 2: the box of ou + 1
-        }
-    }
-    const bool manual = !flags.useTma;
-
+    auto now = [] {
+        unsigned long long t;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+        return t;
+    };
+    unsigned long long* const dbg = a.dbg ? a.dbg + 16 * (size_t)(blockIdx.y * gridDim.x + blockIdx.x) : nullptr;
     if (tid == 0) {
-        mbarInit(&barY, 1);
-        mbarInit(&barC, 1);
+        mbarInit(&barY, NT);  // every thread arrives once its own cp.async copies of the luma box have landed
+        mbarInit(&barC, 1);   // the elected thread arrives with the byte count of the chroma TMA box
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    __syncthreads();
-
-    // chroma box of pass `pass` (0: displacement ou & ~1, 1: + 2) and the luma box of window column w
-    auto chromaOrigin = [&](int w, int pass, int& ca, int& sh, int& rbc) {
-        const int cb = U0 + w * G::SEGW + (ouW[w] & ~1) + 2 * pass;
-        ca = cb & ~15;
-        sh = cb - ca;
-        rbc = (V0 + ovW[w] + LO) >> 1;
-    };
-    auto lumaOrigin = [&](int w, int& ca, int& sh, int& rb) {
-        const int cb = U0 + w * G::SEGW + ouW[w];
-        ca = cb & ~15;
-        sh = cb - ca;
-        rb = V0 + ovW[w] + LO;
-    };
-    auto issueChroma = [&](int pass) {  // thread 0
-        unsigned bytes = 0;
-#pragma unroll
-        for (int w = 0; w < NWIN; ++w)
-            if (existW[w] && (pass == 0 || (ouW[w] & 1))) bytes += G::ROWSC * G::BW;
-        mbarExpectTx(&barC, bytes);
-#pragma unroll
-        for (int w = 0; w < NWIN; ++w)
-            if (existW[w] && (pass == 0 || (ouW[w] & 1))) {
-                int ca, sh, rbc;
-                chromaOrigin(w, pass, ca, sh, rbc);
-                tmaLoad2d(bufC(w), &mapC, ca, rbc, &barC);
-            }
-    };
-    auto stageChromaManual = [&](int pass, bool all) {  // all threads: patch (or fully stage) the chroma boxes of `pass`
-#pragma unroll
-        for (int w = 0; w < NWIN; ++w)
-            if (existW[w] && (pass == 0 || (ouW[w] & 1))) {
-                int ca, sh, rbc;
-                chromaOrigin(w, pass, ca, sh, rbc);
-                const int segValid = min(G::SEGW, vw.lu - (U0 + w * G::SEGW));
-                const int rowsC = min(G::ROWSC, ((V0 + ovW[w] + LO + rowsNeeded - 1) >> 1) - rbc + 1);
-                patchBox<true>(bufC(w), G::BW, vw.c1, vw.pitch, vw.dimU, vw.dimV >> 1, rbc, ca, rowsC, sh, min(sh + segValid + 4, G::BW), all, tid, NT);
-            }
-    };
-
-    if (!manual && tid == 0) {
-        issueChroma(0);
-        unsigned bytes = 0;
-#pragma unroll
-        for (int w = 0; w < NWIN; ++w)
-            if (existW[w]) bytes += G::ROWS * G::BW;
-        mbarExpectTx(&barY, bytes);
-#pragma unroll
-        for (int w = 0; w < NWIN; ++w)
-            if (existW[w]) {
-                int ca, sh, rb;
-                lumaOrigin(w, ca, sh, rb);
-                tmaLoad2d(bufY(w), &mapY, ca, rb, &barY);
-            }
-    }
-
-    // this lane's column and run
-    const int win = NWIN == 1 ? 0 : lane >> 4;
-    const int lw = NWIN == 1 ? lane : lane & 15;
-    const int cu = U0 + 4 * lane, v0 = V0 + 32 * warp;
-    const bool segOk = existW[win] && v0 < vw.lv;                  // this lane's window column has rows in this warp
-    const bool runOk = segOk && cu < vw.lu;                        // (lu is a multiple of 4: words are never partial)
-    const int np = min(32, vw.lv - v0);                            // rows of the run (even)
-    const int ou = ouW[win], ov = ovW[win];
-    const int pi = ov & 1;
-    const bool segOdd = (ou & 1) != 0;
-
-    uint32_t accY[16], accC[16];
-#pragma unroll
-    for (int z = 0; z < 16; ++z) accY[z] = accC[z] = 0;
-
-    if (manual || border) {
-        if (!manual) {
-            mbarWait(&barC, 0);
-            mbarWait(&barY, 0);
+        if (dbg) {
+            unsigned smid;
+            asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+            dbg[0] = now();
+            dbg[4] = smid;
+            dbg[5] = blockIdx.x;
+            dbg[6] = blockIdx.y;
         }
-        stageChromaManual(0, manual);
-#pragma unroll
-        for (int w = 0; w < NWIN; ++w)
-            if (existW[w]) {
-                int ca, sh, rb;
-                lumaOrigin(w, ca, sh, rb);
-                const int segValid = min(G::SEGW, vw.lu - (U0 + w * G::SEGW));
-                patchBox<false>(bufY(w), G::BW, vw.y1, vw.pitch, vw.dimU, vw.dimV, rb, ca, rowsNeeded, sh, min(sh + segValid + 4, G::BW), manual, tid, NT);
-            }
-        __syncthreads();
     }
+    for (int i = tid; i < 128; i += NT) s_red[i >> 4][i & 15] = 0;
+
+    // ---- A. displacements of the tile's windows -----------------------------------------------------------------------
+    int uniOu = 0, uniOv = 0;  // class 128: the one window of the tile
+    if (C::SPREAD) {
+        for (int i = tid; i < nwu * nwv; i += NT) {
+            const int lwu = i % nwu, lwv = i / nwu;
+            const int wu = (U0 >> WSL) + lwu, wv = (V0 >> WSL) + lwv;
+            int packed = 0;
+            uint8_t st = 2;
+            if ((wu << WSL) < vw.lu && (wv << WSL) < vw.lv) {
+                int ox, oy;
+                loadWindowOffsets<STEP>(a, View<STEP>::wx(wu, wv), View<STEP>::wy(wu, wv), ox, oy);
+                packed = (View<STEP>::ou(ox, oy) & 0xffff) | (View<STEP>::ov(ox, oy) << 16);
+                st = 0;
+            }
+            s_off[i] = packed;
+            s_state[i] = st;
+        }
+    } else {
+        int ox, oy;
+        const int wu = U0 >> wsLog2, wv = V0 >> wsLog2;
+        loadWindowOffsets<STEP>(a, View<STEP>::wx(wu, wv), View<STEP>::wy(wu, wv), ox, oy);
+        uniOu = View<STEP>::ou(ox, oy);
+        uniOv = View<STEP>::ov(ox, oy);
+    }
+    const bool manual = !tp.useTma;
+    unsigned phase = 0;
+    const int cu = U0 + 4 * lane;
+    const bool colOk = cu < vw.lu;   // (lu is a multiple of 4: words are never partial)
 
 #pragma unroll 1
-    for (int pass = 0; pass < 2; ++pass) {
-        if (pass == 1) {
-            if (!anyOdd) break;  // CTA-uniform
-            if (manual || border) {
-                // border tiles stage the ou + 1 boxes with plain loads (they are a small share of the tiles)
-                __syncthreads();  // everybody is done with the chroma boxes of pass 0
-                stageChromaManual(1, true);
-                __syncthreads();
+    for (int round = 0; round <= MAX_ROUNDS; ++round) {
+        // ---- B. the windows of this round and the range of their displacements --------------------------------------
+        const bool slow = tp.forceSlow || round == MAX_ROUNDS;   // per-pixel path for everything still pending
+        int minOu = uniOu, maxOu = uniOu, minOv = uniOv, maxOv = uniOv;
+        if (C::SPREAD) {
+            __syncthreads();  // s_off / s_state of the previous step are visible; nobody reads s_rng or the boxes any more
+            if (tid < 4) s_rng[tid] = (tid & 1) ? INT_MIN : INT_MAX;
+            __syncthreads();
+            {
+                int mn = INT_MAX;
+                for (int i = tid; i < nwu * nwv; i += NT)
+                    if (s_state[i] == 0) mn = min(mn, (int)(short)(s_off[i] & 0xffff));
+                mn = __reduce_min_sync(0xffffffffu, mn);
+                if (lane == 0 && mn != INT_MAX) atomicMin(&s_rng[0], mn);
             }
-        }
-        // ---- chroma of this pass ----
-        if (runOk && (pass == 0 || segOdd)) {
-            if (!manual && !border) mbarWait(&barC, (unsigned)pass);
-            int ca, sh, rbc;
-            chromaOrigin(win, pass, ca, sh, rbc);
-            const uint32_t* __restrict__ q = reinterpret_cast<const uint32_t*>(bufC(win)) + (16 * warp) * G::BWW + (sh >> 2) + lw;
-            const int shBits = (sh & 3) * 8;
-            if (np == 32) {
-                uint32_t f2c[16];
-                const uint8_t* __restrict__ p2 = rowPtr(vw.c2 + cu, vw.pitch, v0 >> 1);
-#pragma unroll
-                for (int k = 0; k < 16; ++k) f2c[k] = __ldg(reinterpret_cast<const uint32_t*>(rowPtr(p2, vw.pitch, k)));
-                if (shBits == 0 && !flags.forceFunnel) {
-                    if (pi)
-                        slideChroma<R, 1>(accC, f2c, [&](int j) { return q[j * G::BWW]; });
-                    else
-                        slideChroma<R, 0>(accC, f2c, [&](int j) { return q[j * G::BWW]; });
-                } else {
-                    if (pi)
-                        slideChroma<R, 1>(accC, f2c, [&](int j) { return __funnelshift_r(q[j * G::BWW], q[j * G::BWW + 1], shBits); });
-                    else
-                        slideChroma<R, 0>(accC, f2c, [&](int j) { return __funnelshift_r(q[j * G::BWW], q[j * G::BWW + 1], shBits); });
-                }
-            } else {
-                // partial run at the last rows of the flow field: compact loop, one (row pair, candidate) at a time
-                const int amin = (pi + LO) >> 1;
-                for (int k = 0; k < (np >> 1); ++k) {
-                    const uint32_t f2 = __ldg(reinterpret_cast<const uint32_t*>(rowPtr(vw.c2 + cu, vw.pitch, (v0 >> 1) + k)));
-#pragma unroll
-                    for (int z = 0; z < R; ++z) {
-                        const int d = pi + candOffset<R>(z);
-                        const int j = k + (d >> 1) - amin;
-                        accC[z] = sad4(__funnelshift_r(q[j * G::BWW], q[j * G::BWW + 1], shBits), f2, accC[z]);
-                        if (d & 1) accC[z] = sad4(__funnelshift_r(q[(j + 1) * G::BWW], q[(j + 1) * G::BWW + 1], shBits), f2, accC[z]);
+            __syncthreads();
+            minOu = s_rng[0];
+            if (minOu == INT_MAX) break;  // nothing pending (CTA-uniform)
+            const int limU = slow ? INT_MAX : minOu + C::SU;
+            {
+                int mn = INT_MAX;
+                for (int i = tid; i < nwu * nwv; i += NT)
+                    if (s_state[i] == 0 && (int)(short)(s_off[i] & 0xffff) <= limU) mn = min(mn, s_off[i] >> 16);
+                mn = __reduce_min_sync(0xffffffffu, mn);
+                if (lane == 0 && mn != INT_MAX) atomicMin(&s_rng[2], mn);
+            }
+            __syncthreads();
+            minOv = s_rng[2];
+            const int limV = slow ? INT_MAX : minOv + C::SV;
+            {
+                int mxU = INT_MIN, mxV = INT_MIN;
+                for (int i = tid; i < nwu * nwv; i += NT) {
+                    const int ou = (int)(short)(s_off[i] & 0xffff), ov = s_off[i] >> 16;
+                    if (s_state[i] == 0 && ou <= limU && ov >= minOv && ov <= limV) {
+                        s_state[i] = 1;
+                        mxU = max(mxU, ou);
+                        mxV = max(mxV, ov);
                     }
                 }
+                mxU = __reduce_max_sync(0xffffffffu, mxU);
+                mxV = __reduce_max_sync(0xffffffffu, mxV);
+                if (lane == 0 && mxU != INT_MIN) {
+                    atomicMax(&s_rng[1], mxU);
+                    atomicMax(&s_rng[3], mxV);
+                }
             }
+            __syncthreads();
+            maxOu = s_rng[1];
+            maxOv = s_rng[3];
+        } else {
+            if (round > 0) break;
+            __syncthreads();  // barriers and s_red are initialised
         }
-        if (pass == 0) {
-            if (anyOdd && !(manual || border)) {
-                __syncthreads();  // everybody is done with the chroma boxes of pass 0: the ou + 1 boxes may overwrite them
-                if (tid == 0) issueChroma(1);
+        const bool staged = !slow;
+
+        // ---- C. stage the frame-1 boxes of the round ------------------------------------------------------------------
+        // luma box: plane rows rb .., bytes ca ..; chroma box: chroma rows rbc .., bytes caC ..
+        const int cbMin = U0 + minOu;
+        const int ca = cbMin & ~15;
+        const int rb = V0 + minOv + LO;
+        const int cbMinC = U0 + (minOu & ~1);
+        const int caC = cbMinC & ~15;
+        const int rbc = rb >> 1;
+        const int rowsNeeded = tileRows + SPAN + (maxOv - minOv);               // luma rows of the box that are ever read
+        const int rowsNeededC = ((rb + rowsNeeded - 1) >> 1) - rbc + 1;
+        const int colEnd = cbMin - ca + tileCols + (maxOu - minOu) + 4;         // bytes [cbMin - ca, colEnd) of a luma row are read
+        const int colEndC = cbMinC - caC + tileCols + ((maxOu & ~1) - (minOu & ~1)) + 2 + 4;
+        const bool border = cbMin < 0 || cbMin + tileCols + (maxOu - minOu) + 2 > vw.dimU || rb < 0 || rb + rowsNeeded > vw.dimV;
+        const bool asyncStage = staged && !manual && !border;   // CTA-uniform
+        if (staged && asyncStage) {
+            // interior tile: the chroma box through the TMA engine (one elected thread), the luma box through the LSU path as
+            // 16-byte cp.async copies of all threads — both in flight at once, each completing on its own mbarrier
+            if (tid == 0) {
+                mbarExpectTx(&barC, (unsigned)(tp.boxHC * BW));
+                tmaLoad2d(bufC, &mapC, caC, rbc, &barC);
             }
-            // ---- luma (the copy of the pass-1 chroma boxes is in flight meanwhile) ----
-            if (runOk) {
-                if (!manual && !border) mbarWait(&barY, 0);
-                int ca, sh, rb;
-                lumaOrigin(win, ca, sh, rb);
-                const uint32_t* __restrict__ q = reinterpret_cast<const uint32_t*>(bufY(win)) + (32 * warp) * G::BWW + (sh >> 2) + lw;
-                const int shBits = (sh & 3) * 8;
-                if (np == 32) {
-                    uint32_t f2[32];
-                    const uint8_t* __restrict__ p2 = rowPtr(vw.y2 + cu, vw.pitch, v0);
+            const int cpr = (min(colEnd, BW) + 15) >> 4;  // 16-byte chunks of a luma row that are read
+            const uint8_t* __restrict__ src = vw.y1 + ca;
+            for (int i = tid; i < rowsNeeded * cpr; i += NT) {
+                const int r = i / cpr, c = i - r * cpr;
+                cpAsync16(bufY + r * BW + 16 * c, rowPtr(src, vw.pitch, rb + r) + 16 * c);
+            }
+            asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"((unsigned)__cvta_generic_to_shared(&barY)) : "memory");
+        } else if (staged) {
+            // tile at the frame border (or no TMA): plain loads through the mirror
+            const MirrorBox<true> mc(bufC, BW, vw.c1, vw.pitch, vw.dimU, vw.dimV >> 1, rbc, caC, rowsNeededC, cbMinC - caC, min(colEndC, BW));
+            const MirrorBox<false> my(bufY, BW, vw.y1, vw.pitch, vw.dimU, vw.dimV, rb, ca, rowsNeeded, cbMin - ca, min(colEnd, BW));
+            mc.issue(tid, NT);
+            my.issue(tid, NT);
+            cpAsyncWaitAll();
+            __syncthreads();
+            mc.fixup(tid, NT);
+            my.fixup(tid, NT);
+            __syncthreads();
+        }
+        const bool waitTma = asyncStage;
+        const unsigned parity = phase & 1u;   // the barriers complete one phase per asynchronously staged round
+        if (asyncStage) ++phase;
+        bool waitedC = false, waitedY = false;
+        if (dbg && tid == 0) {
+            if (waitTma) {
+                mbarWait(&barC, parity);
+                mbarWait(&barY, parity);
+                waitedC = waitedY = true;
+            }
+            dbg[1] = now();
+            dbg[7] = round + 1 + (border ? 100 : 0);
+        }
+
+        // ---- D. the runs of this lane -----------------------------------------------------------------------------------
+#pragma unroll 1
+        for (int run = 0; run < C::NRUN; ++run) {
+            const int v0 = V0 + 32 * warp + run * RUN;
+            const bool rowOk = v0 < vw.lv;           // warp-uniform
+            const int np = min(RUN, vw.lv - v0);     // rows of the run (even)
+            // the window of this lane in this run, its state and its displacement
+            const int wu = cu >> wsLog2, wv = v0 >> wsLog2;
+            const bool winThere = rowOk && (wu << wsLog2) < vw.lu;   // the lane's window exists (its own column may not)
+            int ou = uniOu, ov = uniOv;
+            bool active = winThere;
+            if (C::SPREAD && winThere) {
+                const int li = (wv - (V0 >> WSL)) * nwu + (wu - (U0 >> WSL));
+                active = s_state[li] == 1;
+                const int packed = s_off[li];
+                ou = (int)(short)(packed & 0xffff);
+                ov = packed >> 16;
+            }
+            if (C::SPREAD && !__any_sync(0xffffffffu, active)) continue;  // nothing of this warp's run belongs to the round
+            const bool runOk = active && colOk;
+            const int pi = ov & 1;
+            const bool odd = (ou & 1) != 0;
+            uint32_t acc[16];
 #pragma unroll
-                    for (int p = 0; p < 32; ++p) f2[p] = __ldg(reinterpret_cast<const uint32_t*>(rowPtr(p2, vw.pitch, p)));
-                    if (shBits == 0 && !flags.forceFunnel)
-                        slideLuma<R>(accY, f2, [&](int j) { return q[j * G::BWW]; });
-                    else
-                        slideLuma<R>(accY, f2, [&](int j) { return __funnelshift_r(q[j * G::BWW], q[j * G::BWW + 1], shBits); });
-                } else {
-                    for (int p = 0; p < np; ++p) {
-                        const uint32_t f2 = __ldg(reinterpret_cast<const uint32_t*>(rowPtr(vw.y2 + cu, vw.pitch, v0 + p)));
+            for (int z = 0; z < 16; ++z) acc[z] = 0;
+
+            if (runOk && staged && np == RUN) {
+                // frame 2 of the run first: these loads are in flight while the TMA boxes land
+                uint32_t f2c[RUN / 2], f2[RUN];
+                {
+                    const uint8_t* __restrict__ pc = rowPtr(vw.c2 + cu, vw.pitch, v0 >> 1);
+#pragma unroll
+                    for (int k = 0; k < RUN / 2; ++k) f2c[k] = __ldg(reinterpret_cast<const uint32_t*>(rowPtr(pc, vw.pitch, k)));
+                    const uint8_t* __restrict__ py = rowPtr(vw.y2 + cu, vw.pitch, v0);
+#pragma unroll
+                    for (int p = 0; p < RUN; ++p) f2[p] = __ldg(reinterpret_cast<const uint32_t*>(rowPtr(py, vw.pitch, p)));
+                }
+                uint32_t accC[16];
+#pragma unroll
+                for (int z = 0; z < 16; ++z) accC[z] = 0;
+                // chroma: one pass (ou even) or two passes 2 bytes apart (ou odd)
+                if (waitTma && !waitedC) {
+                    mbarWait(&barC, parity);
+                    waitedC = true;
+                }
+                {
+                    const int offC = cu + (ou & ~1) - caC;
+                    const int rowC0 = ((v0 + ov + LO) >> 1) - rbc;
+                    const uint32_t* __restrict__ q0 = reinterpret_cast<const uint32_t*>(bufC + rowC0 * BW + (offC & ~3));
+                    const int sh0 = (offC & 3) * 8;
+                    const uint32_t* __restrict__ q1 = reinterpret_cast<const uint32_t*>(bufC + rowC0 * BW + ((offC + 2) & ~3));
+                    const int sh1 = ((offC + 2) & 3) * 8;
+                    if (pi) {
+                        slideChroma<R, RUN, 1>(accC, f2c, [&](int j) { return __funnelshift_r(q0[j * BWW], q0[j * BWW + 1], sh0); });
+                        if (odd) slideChroma<R, RUN, 1>(accC, f2c, [&](int j) { return __funnelshift_r(q1[j * BWW], q1[j * BWW + 1], sh1); });
+                    } else {
+                        slideChroma<R, RUN, 0>(accC, f2c, [&](int j) { return __funnelshift_r(q0[j * BWW], q0[j * BWW + 1], sh0); });
+                        if (odd) slideChroma<R, RUN, 0>(accC, f2c, [&](int j) { return __funnelshift_r(q1[j * BWW], q1[j * BWW + 1], sh1); });
+                    }
+                }
+                // luma
+                if (waitTma && !waitedY) {
+                    mbarWait(&barY, parity);
+                    waitedY = true;
+                }
+                {
+                    const int offY = cu + ou - ca;
+                    const int rowY0 = v0 + ov + LO - rb;
+                    const uint32_t* __restrict__ q = reinterpret_cast<const uint32_t*>(bufY + rowY0 * BW + (offY & ~3));
+                    const int sh = (offY & 3) * 8;
+                    slideLuma<R, RUN>(acc, f2, [&](int j) { return __funnelshift_r(q[j * BWW], q[j * BWW + 1], sh); });
+                }
+                // chroma weight = (rows coincide ? 2 : 1) * (columns coincide ? 2 : 1)
+                const int evenU = odd ? 0 : 1;
+#pragma unroll
+                for (int z = 0; z < R; ++z) acc[z] += accC[z] << (chromaShift<R>(pi, z) + evenU);
+            } else if (runOk && staged) {
+                // partial run at the last rows of the flow field: compact loops, one (row, candidate) at a time
+                if (waitTma && !waitedC) {
+                    mbarWait(&barC, parity);
+                    waitedC = true;
+                }
+                if (waitTma && !waitedY) {
+                    mbarWait(&barY, parity);
+                    waitedY = true;
+                }
+                const int offC = cu + (ou & ~1) - caC;
+                const int rowC0 = ((v0 + ov + LO) >> 1) - rbc;
+                const int amin = (pi + LO) >> 1;
+                const int evenU = odd ? 0 : 1;
+                for (int pass = 0; pass < (odd ? 2 : 1); ++pass) {
+                    const uint32_t* __restrict__ q = reinterpret_cast<const uint32_t*>(bufC + rowC0 * BW + ((offC + 2 * pass) & ~3));
+                    const int sh = ((offC + 2 * pass) & 3) * 8;
+                    for (int k = 0; k < (np >> 1); ++k) {
+                        const uint32_t f2 = __ldg(reinterpret_cast<const uint32_t*>(rowPtr(vw.c2 + cu, vw.pitch, (v0 >> 1) + k)));
 #pragma unroll
                         for (int z = 0; z < R; ++z) {
-                            const int j = p + candOffset<R>(z) - LO;
-                            accY[z] = sad4(__funnelshift_r(q[j * G::BWW], q[j * G::BWW + 1], shBits), f2, accY[z]);
+                            const int d = pi + candOffset<R>(z);
+                            const int j = k + (d >> 1) - amin;
+                            uint32_t sd = sad4(__funnelshift_r(q[j * BWW], q[j * BWW + 1], sh), f2, 0u);
+                            if (d & 1) sd = sad4(__funnelshift_r(q[(j + 1) * BWW], q[(j + 1) * BWW + 1], sh), f2, sd);
+                            acc[z] += sd << (((d & 1) ? 0 : 1) + evenU);
                         }
                     }
                 }
-            }
-        }
-    }
-
-    // ---- combine luma and chroma: chroma weight = (rows coincide ? 2 : 1) * (columns coincide ? 2 : 1) ----
-    const int evenU = segOdd ? 0 : 1;
-    uint32_t acc[16];
+                const int offY = cu + ou - ca;
+                const int rowY0 = v0 + ov + LO - rb;
+                const uint32_t* __restrict__ q = reinterpret_cast<const uint32_t*>(bufY + rowY0 * BW + (offY & ~3));
+                const int sh = (offY & 3) * 8;
+                for (int p = 0; p < np; ++p) {
+                    const uint32_t f2 = __ldg(reinterpret_cast<const uint32_t*>(rowPtr(vw.y2 + cu, vw.pitch, v0 + p)));
 #pragma unroll
-    for (int z = 0; z < 16; ++z) {
-        const int sh = z < R ? (pi ? chromaShift<R, 1>(z < R ? z : 0) : chromaShift<R, 0>(z < R ? z : 0)) + evenU : 0;
-        acc[z] = accY[z] + (accC[z] << sh);
+                    for (int z = 0; z < R; ++z) {
+                        const int j = p + candOffset<R>(z) - LO;
+                        acc[z] = sad4(__funnelshift_r(q[j * BWW], q[j * BWW + 1], sh), f2, acc[z]);
+                    }
+                }
+            } else if (runOk) {
+                // per-pixel path straight from the planes
+                for (int i = 0; i < 4; ++i) {
+                    const int fu = mirrorSearch(cu + i + ou, vw.dimU);
+                    for (int p = 0; p < np; ++p) {
+                        const uint32_t f2 = fetchPixel(vw.y2, vw.c2, vw.pitch, v0 + p, cu + i);
+                        const int bv = v0 + p + ov;
+#pragma unroll
+                        for (int z = 0; z < R; ++z) acc[z] = sad4(fetchPixel(vw.y1, vw.c1, vw.pitch, mirrorSearch(bv + candOffset<R>(z), vw.dimV), fu), f2, acc[z]);
+                    }
+                }
+            }
+
+            // ---- E. reduce over the window's lanes and finalize ----------------------------------------------------------
+            const bool b0 = lane & 1, b1 = lane & 2, b2 = lane & 4, b3 = lane & 8;
+            if (WSC <= 32) {
+                // the window lives in SEG lanes of this warp: butterfly over them, every lane then owns NZ layers
+                constexpr int NZ = 16 / C::SEG;
+                if (C::SEG >= 2) bfly<16>(acc, 1, b0);
+                if (C::SEG >= 4) bfly<8>(acc, 2, b1);
+                if (C::SEG >= 8) bfly<4>(acc, 4, b2);
+                const int zbase = (C::SEG >= 2 && b0 ? 8 : 0) + (C::SEG >= 4 && b1 ? 4 : 0) + (C::SEG >= 8 && b2 ? 2 : 0);
+                const int wx = View<STEP>::wx(wu, wv), wy = View<STEP>::wy(wu, wv);
+                uint32_t bestT = 0xffffffffu;
+                int bestZ = zbase < R ? zbase : 0xff;  // no layer beats a sum of 2^32-1: the lane's first layer stands, as with strict <
+                WindowCtx c;
+                c.o = 0;
+                if (active) {
+                    // (lanes of a window past the last column still finalize their layers)
+                    c = loadWindowCtx<STEP>(a, wx, wy, STEP == 1 ? ou : ov, STEP == 1 ? ov : ou);
+#pragma unroll
+                    for (int i = 0; i < NZ; ++i) {
+                        const int z = zbase + i;
+                        if (z < R) {
+                            const uint32_t total = layerTotalOf(a, c, acc[i], signedSquare(z - R / 2));
+                            tapTotal<R>(a, wx, wy, z, total);
+                            if (total < bestT) {  // z ascends inside a lane: strict < keeps the lowest layer of a tie
+                                bestT = total;
+                                bestZ = z;
+                            }
+                        }
+                    }
+                }
+                unsigned long long best = layerKey(bestT, bestZ);
+                if (C::SEG >= 2) best = min(best, shflXor64(best, 1));
+                if (C::SEG >= 4) best = min(best, shflXor64(best, 2));
+                if (C::SEG >= 8) best = min(best, shflXor64(best, 4));
+                if (active && (lane & (C::SEG - 1)) == 0) commitWindow<R, STEP>(a, wx, wy, c.o, (int)(best & 0xff));
+            } else {
+                // windows of 64 pixels and more: sums of the CTA in shared memory first
+                bfly<16>(acc, 1, b0);
+                bfly<8>(acc, 2, b1);
+                bfly<4>(acc, 4, b2);
+                bfly<2>(acc, 8, b3);
+                uint32_t sm = acc[0];
+                const int z = (b0 ? 8 : 0) + (b1 ? 4 : 0) + (b2 ? 2 : 0) + (b3 ? 1 : 0);  // the layer this lane ended up with
+                int lwin = 0;
+                if (WSC == 64) {
+                    lwin = (lane >> 4) + 2 * ((32 * warp) >> 6);  // window of the tile: 2 across, TV / 64 down
+                } else {
+                    sm += __shfl_xor_sync(0xffffffffu, sm, 16);
+                }
+                if (active && z < R && (WSC == 64 || lane < 16)) atomicAdd(&s_red[lwin][z], sm);
+            }
+        }
+
+        if (C::SPREAD) {
+            __syncthreads();  // every lane is done with the round's boxes and states
+            for (int i = tid; i < nwu * nwv; i += NT)
+                if (s_state[i] == 1) s_state[i] = 2;
+        }
     }
 
-    // ---- reduce over the lanes of the window column, add to the window's scratch, last contributor finalizes ----
-    const bool b0 = lane & 1, b1 = lane & 2, b2 = lane & 4, b3 = lane & 8;
-    bfly<16>(acc, 1, b0);
-    bfly<8>(acc, 2, b1);
-    bfly<4>(acc, 4, b2);
-    bfly<2>(acc, 8, b3);
-    uint32_t s = acc[0];
-    if (NWIN == 1) s += __shfl_xor_sync(0xffffffffu, s, 16);
-    const int z = (b0 ? 8 : 0) + (b1 ? 4 : 0) + (b2 ? 2 : 0) + (b3 ? 1 : 0);  // the layer this lane ended up with
-    const bool holder = (NWIN == 1 ? lane < 16 : true) && z < R;             // one lane per (window column, layer)
-    const int uw = U0 + win * G::SEGW;
-    const int wu = uw >> a.wsLog2;
-    const int wx = View<STEP>::wx(wu, wv), wy = View<STEP>::wy(wu, wv);
-    const size_t widx = (size_t)(wy * a.nWx + wx);
-    bool last = false;
-    if (segOk) {
-        if (holder) atomicAdd(&a.winSums[widx * 16 + z], s);
-        __threadfence();
+    if (dbg) {
+        __syncthreads();
+        if (tid == 0) dbg[2] = now();
     }
-    __syncwarp();
-    {
-        unsigned ticket = 0, need = 1;
-        if (segOk && lw == 0) {
-            const int uext = min(a.ws, vw.lu - (wu << a.wsLog2)), vext = min(a.ws, vw.lv - (wv << a.wsLog2));
-            need = (unsigned)(((uext + G::SEGW - 1) / G::SEGW) * ((vext + 31) >> 5));
-            ticket = atomicAdd(&a.winTicket[widx], 1u);
-        }
-        const int leader = NWIN == 1 ? 0 : (lane & 16);
-        ticket = __shfl_sync(0xffffffffu, ticket, leader);
-        need = __shfl_sync(0xffffffffu, need, leader);
-        last = segOk && ticket == need - 1;
-    }
-    uint32_t sum = 0;
-    if (last) {
-        __threadfence();
-        if (holder) {
-            sum = __ldcg(&a.winSums[widx * 16 + z]);
-            a.winSums[widx * 16 + z] = 0;  // scratch and ticket are left zeroed for the next pass
-        }
-        if (lw == 0) a.winTicket[widx] = 0;
-    }
-    WindowCtx c;
-    c.o = 0; c.nw = 0; c.useNb = false;
-    c.nb[0] = c.nb[1] = c.nb[2] = c.nb[3] = 0;
-    unsigned long long key = ~0ull;
-    if (last) {
-        int ox, oy;
-        loadWindowOffsets<STEP>(a, wx, wy, ox, oy);
-        c = loadWindowCtx<STEP>(a, wx, wy, ox, oy);
-        if (z < R) {
-            const uint32_t total = windowTotal<R>(a, c, sum, z);
-            if (holder) {
-                tapTotal<R>(a, wx, wy, z, total);
-                key = layerKey(total, z);
+    if (WSC >= 64) {
+        __syncthreads();
+        if (WSC == 64) {
+            // every window of the tile is complete inside the CTA: one thread per window finalizes it
+            const int nWin = 2 * (TV >> 6);
+            if (tid < nWin) {
+                const int wu = (U0 >> 6) + (tid & 1), wv = (V0 >> 6) + (tid >> 1);
+                const int wx = View<STEP>::wx(wu, wv), wy = View<STEP>::wy(wu, wv);
+                if ((wu << 6) < vw.lu && (wv << 6) < vw.lv) finalizeWindow<R, STEP>(a, wx, wy, s_red[tid]);
+            }
+        } else {
+            // add the CTA's sums to the window's scratch; the LAST CTA to arrive (ticket) finds them complete, finalizes the
+            // window and leaves scratch and ticket zeroed for the next pass — no finalize kernel, no memset between passes
+            const int wu = U0 >> wsLog2, wv = V0 >> wsLog2;
+            const int wx = View<STEP>::wx(wu, wv), wy = View<STEP>::wy(wu, wv);
+            const size_t widx = (size_t)(wy * a.nWx + wx);
+            if (warp == 0) {
+                if (lane < R) atomicAdd(&a.winSums[widx * 16 + lane], s_red[0][lane]);
+                __threadfence();
+                __syncwarp();
+                int last = 0;
+                if (lane == 0) {
+                    const int uext = min(a.ws, vw.lu - (wu << wsLog2)), vext = min(a.ws, vw.lv - (wv << wsLog2));
+                    const unsigned need = (unsigned)(((uext + 127) >> 7) * ((vext + TV - 1) / TV));
+                    last = atomicAdd(&a.winTicket[widx], 1u) == need - 1;
+                }
+                last = __shfl_sync(0xffffffffu, last, 0);
+                if (last) {
+                    __threadfence();
+                    uint32_t sum = 0;
+                    if (lane < R) {
+                        sum = __ldcg(&a.winSums[widx * 16 + lane]);
+                        a.winSums[widx * 16 + lane] = 0;
+                    }
+                    if (lane == 0) a.winTicket[widx] = 0;
+                    int ox, oy;
+                    loadWindowOffsets<STEP>(a, wx, wy, ox, oy);
+                    const WindowCtx c = loadWindowCtx<STEP>(a, wx, wy, ox, oy);
+                    unsigned long long key = ~0ull;
+                    if (lane < R) {
+                        const uint32_t total = windowTotal<R>(a, c, sum, lane);
+                        tapTotal<R>(a, wx, wy, lane, total);
+                        key = layerKey(total, lane);
+                    }
+                    key = min(key, shflXor64(key, 1));
+                    key = min(key, shflXor64(key, 2));
+                    key = min(key, shflXor64(key, 4));
+                    key = min(key, shflXor64(key, 8));
+                    if (lane == 0) commitWindow<R, STEP>(a, wx, wy, c.o, (int)(key & 0xff));
+                }
             }
         }
     }
-    key = min(key, shflXor64(key, 1));
-    key = min(key, shflXor64(key, 2));
-    key = min(key, shflXor64(key, 4));
-    key = min(key, shflXor64(key, 8));
-    if (last && lw == 0) commitWindow<R, STEP>(a, wx, wy, c.o, (int)(key & 0xff));
+    if (dbg) {
+        __syncthreads();
+        if (tid == 0) dbg[3] = now();
+    }
 }
 
 // ---- tensor maps ------------------------------------------------------------------------------------------------------
@@ -510,7 +709,7 @@ const CUtensorMap* tensorMapFor(hrb_ofc* h, const uint8_t* base, int dimU, int d
     for (auto* e : h->tmaCache->entries)
         if (e->base == base && e->dimU == dimU && e->dimV == dimV && e->pitch == pitch && e->boxW == boxW && e->boxH == boxH) return &e->map;
     EncodeTiledFn enc = encodeTiled();
-    if (!enc) return nullptr;
+    if (!enc || boxH > 256 || boxW > 256) return nullptr;
     auto* e = new TmaCache::Entry();
     const cuuint64_t dims[2] = {(cuuint64_t)dimU, (cuuint64_t)dimV};
     const cuuint64_t strides[1] = {(cuuint64_t)pitch};
@@ -522,7 +721,7 @@ const CUtensorMap* tensorMapFor(hrb_ofc* h, const uint8_t* base, int dimU, int d
         return nullptr;
     }
     e->base = base; e->dimU = dimU; e->dimV = dimV; e->pitch = pitch; e->boxW = boxW; e->boxH = boxH;
-    if (h->tmaCache->entries.size() >= 256) {  // geometry and slots are fixed per handle: this never grows in practice
+    if (h->tmaCache->entries.size() >= 512) {  // geometry and slots are fixed per handle: this never grows in practice
         for (auto* o : h->tmaCache->entries) delete o;
         h->tmaCache->entries.clear();
     }
@@ -530,45 +729,98 @@ const CUtensorMap* tensorMapFor(hrb_ofc* h, const uint8_t* base, int dimU, int d
     return &e->map;
 }
 
-template <int R, int STEP, int NWV, int NWIN> int launchSlide(hrb_ofc* h, const SearchArgs& a) {
-    using G = SlideGeom<R, NWV, NWIN>;
-    static std::once_flag configured[HRB_MAX_DEVICES];  // the attribute is per device
-    cudaError_t cfgErr = cudaSuccess;
-    std::call_once(configured[h->device & (HRB_MAX_DEVICES - 1)],
-                   [&] { cfgErr = cudaFuncSetAttribute(sadSlidePlanarKernel<R, STEP, NWV, NWIN>, cudaFuncAttributeMaxDynamicSharedMemorySize, G::SMEM); });
-    HRB_CUDA(cfgErr);
+// shared memory of a CTA with nwv warps: the two boxes (each staged as two TMA boxes) + the per-window displacements
+template <int R, int WSC> TileParams tileParams(int nwv) {
+    using C = Cls<WSC>;
+    TileParams tp;
+    tp.nwv = nwv;
+    const int rowsY = 32 * nwv + CandSpan<R>::SPAN + C::SV;
+    tp.rowsY = rowsY;
+    tp.boxHC = rowsY / 2 + 2;
+    tp.lumaBytes = align128(rowsY * C::BW);
+    tp.chromaBytes = align128(tp.boxHC * C::BW);
+    tp.useTma = 1;
+    tp.forceSlow = 0;
+    return tp;
+}
+template <int WSC> int tileSmem(const TileParams& tp) {
+    const int nWin = Cls<WSC>::SPREAD ? (128 / WSC) * ((32 * tp.nwv) / WSC) : 0;
+    return tp.lumaBytes + tp.chromaBytes + nWin * 4 + ((nWin + 15) & ~15) + 128;  // boxes, window displacements, window states, alignment slack
+}
+
+// Warps per CTA (tile rows / 32): the choice that needs the fewest rounds of resident CTAs, then the smallest halo share.
+template <int R, int WSC> int chooseWarps(const hrb_ofc* h, int lu, int lv) {
+    if (WSC >= 128) return 4;
+    int best = 4;
+    double bestCost = 1e30;
+    for (int nwv = 2; nwv <= 6; ++nwv) {
+        if (WSC == 64 && (nwv & 1)) continue;  // the tile holds whole window rows
+        if (WSC == 64 && nwv > 4) continue;    // s_red holds 8 windows
+        const TileParams tp = tileParams<R, WSC>(nwv);
+        if (tp.boxHC > 256) continue;
+        const int smem = tileSmem<WSC>(tp);
+        const int perSm = min(min((233472) / (smem + 1040), 3), 2048 / (32 * nwv));  // __launch_bounds__(192, 3)
+        if (perSm < 1) continue;
+        const long tiles = (long)((lu + 127) / 128) * ((lv + 32 * nwv - 1) / (32 * nwv));
+        const long slots = (long)h->smCount * perSm;
+        const long rounds = (tiles + slots - 1) / slots;
+        // a round costs the tile's rows plus the candidate span; few resident warps hide latency badly
+        const double cost = (double)rounds * (32 * nwv + CandSpan<R>::SPAN) * (1.0 + 2.0 / (perSm * nwv));
+        if (cost < bestCost) {
+            bestCost = cost;
+            best = nwv;
+        }
+    }
+    return best;
+}
+
+template <int R, int STEP, int WSC> int launchTile(hrb_ofc* h, const SearchArgs& a) {
+    using C = Cls<WSC>;
     const int lu = STEP == 1 ? a.lw : a.lh, lv = STEP == 1 ? a.lh : a.lw;
     const int dimU = STEP == 1 ? a.W : a.H, dimV = STEP == 1 ? a.H : a.W;
     const uint8_t* y1 = STEP == 1 ? a.y1 : a.yT1;
     const uint8_t* c1 = STEP == 1 ? a.c1 : a.cT1;
     const int pitch = STEP == 1 ? a.pitch : a.pitchT;
-    SlideFlags flags;
-    flags.useTma = h->searchVariant != 2;
-    flags.forceFunnel = h->searchVariant == 3;
-    const CUtensorMap* mY = flags.useTma ? tensorMapFor(h, y1, dimU, dimV, pitch, G::BW, G::ROWS) : nullptr;
-    const CUtensorMap* mC = flags.useTma ? tensorMapFor(h, c1, dimU, dimV / 2, pitch, G::BW, G::ROWSC) : nullptr;
+    TileParams tp = tileParams<R, WSC>(chooseWarps<R, WSC>(h, lu, lv));
+    tp.useTma = h->searchVariant != 2;
+    tp.forceSlow = h->searchVariant == 3;
+    const int smem = tileSmem<WSC>(tp);
+    static std::atomic<int> configured[HRB_MAX_DEVICES];  // largest dynamic shared memory size set per device
+    std::atomic<int>& cfg = configured[h->device & (HRB_MAX_DEVICES - 1)];
+    if (cfg.load(std::memory_order_acquire) < smem) {
+        HRB_CUDA(cudaFuncSetAttribute(sadTileKernel<R, STEP, WSC>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        cfg.store(smem, std::memory_order_release);
+    }
+    const CUtensorMap* mC = tp.useTma ? tensorMapFor(h, c1, dimU, dimV / 2, pitch, C::BW, tp.boxHC) : nullptr;
     CUtensorMap dummy;
     memset(&dummy, 0, sizeof(dummy));
-    if (!mY || !mC) {
-        flags.useTma = 0;
-        mY = mC = &dummy;
+    if (!mC) {
+        tp.useTma = 0;
+        mC = &dummy;
     }
-    const dim3 grid((lu + 127) / 128, (lv + 32 * NWV - 1) / (32 * NWV), 1);
-    sadSlidePlanarKernel<R, STEP, NWV, NWIN><<<grid, dim3(32, NWV, 1), G::SMEM, h->stream>>>(a, *mY, *mC, flags);
+    (void)y1;
+    const dim3 grid((lu + 127) / 128, (lv + 32 * tp.nwv - 1) / (32 * tp.nwv), 1);
+    sadTileKernel<R, STEP, WSC><<<grid, dim3(32, tp.nwv, 1), smem, h->stream>>>(a, *mC, tp);
     HRB_LAUNCH_CHECK();
     return HRB_OK;
 }
 
-template <int R, int STEP> int launchSlideStep(hrb_ofc* h, const SearchArgs& a) {
-    if (a.ws >= 128) return launchSlide<R, STEP, 4, 1>(h, a);
-    return launchSlide<R, STEP, 2, 2>(h, a);
+template <int R, int STEP> int launchTileStep(hrb_ofc* h, const SearchArgs& a) {
+    switch (a.ws) {
+        case 4: return launchTile<R, STEP, 4>(h, a);
+        case 8: return launchTile<R, STEP, 8>(h, a);
+        case 16: return launchTile<R, STEP, 16>(h, a);
+        case 32: return launchTile<R, STEP, 32>(h, a);
+        case 64: return launchTile<R, STEP, 64>(h, a);
+        default: return a.ws >= 128 ? launchTile<R, STEP, 128>(h, a) : -1;
+    }
 }
 
-template <int R> int launchSlideR(hrb_ofc* h, const SearchArgs& a, int step) { return step == 1 ? launchSlideStep<R, 1>(h, a) : launchSlideStep<R, 0>(h, a); }
+template <int R> int launchTileR(hrb_ofc* h, const SearchArgs& a, int step) { return step == 1 ? launchTileStep<R, 1>(h, a) : launchTileStep<R, 0>(h, a); }
 
 }  // namespace
 
-// One whole pass for ws >= 64 at full flow resolution.  -1: this (R, geometry) is not covered here.
+// One whole pass for ws >= 4 at full flow resolution.  -1: this (R, geometry) is not covered here.
 // Compiled three times (-DHRB_SLIDE_PART=0/1/2), four search radii per part, so the parts build in parallel.
 #ifndef HRB_SLIDE_PART
 #error "compile with -DHRB_SLIDE_PART=0, 1 or 2"
@@ -577,9 +829,9 @@ template <int R> int launchSlideR(hrb_ofc* h, const SearchArgs& a, int step) { r
 #define HRB_SLIDE_CONCAT(a, b) HRB_SLIDE_CONCAT2(a, b)
 int HRB_SLIDE_CONCAT(launchSearchPassSlidePart, HRB_SLIDE_PART)(hrb_ofc* h, const SearchArgs& a, int R, int step) {
     const int lu = step == 1 ? a.lw : a.lh;
-    if (a.rs != 0 || a.ws < 64 || (lu & 3) != 0) return -1;
+    if (a.rs != 0 || a.ws < 8 || (lu & 3) != 0) return -1;
     switch (R) {
-#define HRB_CASE(N) case N: return launchSlideR<N>(h, a, step);
+#define HRB_CASE(N) case N: return launchTileR<N>(h, a, step);
 #if HRB_SLIDE_PART == 0
         HRB_CASE(5) HRB_CASE(6) HRB_CASE(7) HRB_CASE(8)
 #elif HRB_SLIDE_PART == 1

@@ -277,6 +277,16 @@ class OpticalFlowCalc:
     def setSearchVariant(self, variant):
         self._check(self._lib.hrb_ofc_set_search_variant(self._h, int(variant)))
 
+    def debugTimeline(self, words_per_pass):
+        """Debug aid: per-CTA timelines of the tile search kernels of the following flow calculations (0 = off)."""
+        self._check(self._lib.hrb_ofc_debug_timeline(self._h, int(words_per_pass)))
+
+    def readDebugTimeline(self, words_per_pass, passes=32):
+        import numpy as np
+        buf = np.zeros(words_per_pass * passes, np.uint64)
+        self._check(self._lib.hrb_ofc_debug_timeline_read(self._h, buf.ctypes.data, buf.nbytes))
+        return buf.reshape(passes, words_per_pass // 16, 16)
+
     def setFlowOverlap(self, on):
         """calculateOpticalFlowAsync on its own stream beside the following warps (default) or on the compute stream."""
         self._check(self._lib.hrb_ofc_set_flow_overlap(self._h, 1 if on else 0))
