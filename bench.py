@@ -50,6 +50,28 @@ def metric_name(workload):
 UNIT = "frames/s"
 
 
+def _nolib(name):
+    """hopperrender_b200/<name>.py loaded WITHOUT the package __init__ (which loads libhrb.so): the reference arm must not
+    map the CUDA library.  synth.py and replay.py are plain numpy / python."""
+    import importlib.util
+    key = f"_hrb_nolib_{name}"
+    if key in sys.modules:
+        return sys.modules[key]
+    spec = importlib.util.spec_from_file_location(key, os.path.join(ROOT, "hopperrender_b200", name + ".py"))
+    mod = importlib.util.module_from_spec(spec)
+    sys.modules[key] = mod
+    spec.loader.exec_module(mod)
+    return mod
+
+
+def host_threads():
+    """Threads the CPU legs may use: the cores this process is allowed on (launchers export OMP_NUM_THREADS=1; ignored)."""
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except AttributeError:
+        return max(1, os.cpu_count() or 1)
+
+
 def peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -80,7 +102,7 @@ class ClockSampler:
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "50"],
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "20"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._pump, daemon=True)
             self.thread.start()
@@ -156,7 +178,7 @@ def algorithmic_bytes(wl):
 # ------------------------------------------------------------------------------------------------------
 def cpu_sample_rows(wl, budget_s):
     """Rows of a full-width band of the workload frame whose flow + warps cost about budget_s on this host."""
-    from hopperrender_b200 import synth
+    synth = _nolib("synth")
     from oracle import OracleCalc
     W, hdr = wl["W"], wl["hdr"]
     probe = 128
@@ -178,7 +200,7 @@ def cpu_sample_rows(wl, budget_s):
 
 def cpu_step_runner(wl, rows):
     """Returns (fn, n_out): fn() runs one source-frame step (update + flow + N warps + downloads) on the CPU sample."""
-    from hopperrender_b200 import replay, synth
+    replay, synth = _nolib("replay"), _nolib("synth")
     from oracle import OracleCalc
     W, hdr = wl["W"], wl["hdr"]
     o = OracleCalc(rows, W, 0, 0, 8, 6, 0.0, 255.0, rows, hdr)
@@ -203,12 +225,56 @@ def cpu_step_runner(wl, rows):
     return step
 
 
+def reference_opencl_same_gpu(wl, steps=8, radius=SEARCH_RADIUS):
+    """The reference ITSELF — unmodified HopperRender host classes + OpenCL kernel strings (oracle/_ref) — through the NVIDIA
+    OpenCL driver on this box's GPU, with the filter's call sequence, its blocking transfers and its own event timers
+    (opticalFlowCalcSDR.cpp:119-138, :32-41).  None when oracle/_ref is not built or no OpenCL device accepts it."""
+    try:
+        from oracle import RefCalc, ref_available
+        if not ref_available():
+            return None
+        replay, synth = _nolib("replay"), _nolib("synth")
+        W, H, hdr = wl["W"], wl["H"], wl["hdr"]
+        r = RefCalc(H, W, 0, 0, 8, 6, 0.0, 255.0, wl["maxres"], hdr)
+        r.setParams(searchRadius=radius)
+        frames = [synth.make_frame(W, H, t, synth.SEED_BASE + 2, hdr, noise=False) for t in range(3)]
+        ring = frames + [frames[1]]
+        out = np.zeros(r.outputFrameBytes, np.uint8)
+        for f in frames:
+            r.updateFrame(f)
+        sched = replay.output_schedule(steps + 4, wl["target"], replay.SOURCE_FRAME_TIME_23976)
+
+        def step(i):
+            r.updateFrame(ring[i % 4])
+            r.calculateOpticalFlow()
+            for b in sched[i]:
+                r.warpFrames(b, 2)
+                r.downloadFrame(out)
+            return len(sched[i])
+
+        step(0)
+        t0 = time.perf_counter()
+        n, flow_s, warp_s = 0, [], []
+        for i in range(1, 1 + steps):
+            n += step(i)
+            st = r.state()
+            flow_s.append(st.ofcCalcTime)
+            warp_s.append(st.warpCalcTime)
+        dt = time.perf_counter() - t0
+        res = {"value": n / dt, "unit": UNIT, "ofc_ms": float(np.median(flow_s)) * 1e3, "warp_ms": float(np.median(warp_s)) * 1e3, "steps": steps,
+               "device": r.deviceName(), "api": "reference's own blocking calls (pageable host buffers) and event timers; same GPU, NVIDIA OpenCL"}
+        r.close()
+        return res
+    except Exception as e:  # noqa: BLE001
+        return {"value": None, "unit": UNIT, "error": str(e)[:200]}
+
+
 def run_reference(args, wl, wl_name):
-    from oracle import num_threads
     rank, world, _ = dist_env()
     if rank != 0:
         return
-    cores = num_threads()
+    from oracle import set_num_threads
+    cores = set_num_threads(host_threads())
     per_step = max(0.2, min(8.0, float(os.environ.get("HRB_REF_BUDGET_S", "150")) / max(args.steps + args.warmup, 1)))
     rows = cpu_sample_rows(wl, per_step)
     step = cpu_step_runner(wl, rows)
@@ -232,12 +298,16 @@ def run_reference(args, wl, wl_name):
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
+    if not args.no_cpu_baseline:
+        # beside the CPU port: the reference's own kernels on this box's GPU, when its OpenCL leg is usable here
+        line["reference_opencl_b200"] = reference_opencl_same_gpu(wl, radius=SEARCH_RADIUS)
     print(json.dumps(line), flush=True)
 
 
 def cpu_baseline(wl):
     """Bounded CPU sample for the main line (rank 0, N=1): ~15 s of oracle work."""
-    from oracle import num_threads
+    from oracle import set_num_threads
+    cores = set_num_threads(host_threads())
     rows = cpu_sample_rows(wl, 5.0)
     step = cpu_step_runner(wl, rows)
     step()
@@ -247,7 +317,7 @@ def cpu_baseline(wl):
         frames += step()
     dt = time.perf_counter() - t0
     frac = rows / wl["H"]
-    return {"value": frames * frac / dt, "unit": UNIT, "cores": num_threads(), "kind": "port",
+    return {"value": frames * frac / dt, "unit": UNIT, "cores": cores, "kind": "port",
             "sample": f"2 source-frame steps on a full-width {wl['W']}x{rows} band ({frac:.4f} of the pixels), scaled linearly to the full frame"}
 
 
@@ -359,11 +429,15 @@ def run_streams(args, wl):
         c.m_opticalFlowSearchRadius = args.radius
         if args.no_overlap:
             c.setFlowOverlap(False)
-    RING = 6
+    NFR = 6
+    PING = list(range(NFR)) + list(range(NFR - 2, 0, -1))   # frames played back and forth: every pair is one motion step
+    RING = len(PING)
     tdt = torch.int16 if hdr else torch.uint8
-    host_frames = [synth.make_frame(W, H, t, synth.SEED_BASE + 2 + rank, hdr) for t in range(RING)]
-    pinned = [torch.from_numpy(f.view(np.int16) if hdr else f).pin_memory() for f in host_frames]
-    dev = [p.cuda() for p in pinned]
+    distinct = [synth.make_frame(W, H, t, synth.SEED_BASE + 2 + rank, hdr) for t in range(NFR)]
+    pinned_d = [torch.from_numpy(f.view(np.int16) if hdr else f).pin_memory() for f in distinct]
+    dev_d = [p.cuda() for p in pinned_d]
+    pinned = [pinned_d[t] for t in PING]
+    dev = [dev_d[t] for t in PING]
     torch.cuda.synchronize()
     sched = replay.output_schedule(5 * (args.warmup + args.steps) + 128, wl["target"], replay.SOURCE_FRAME_TIME_23976)
     POOL = 8
@@ -386,10 +460,10 @@ def run_streams(args, wl):
         c.calculateOpticalFlowAsync()
         for b in sched[i]:
             c.warpFrames(b, hr.BlendedFrame)
+            while len(pending[h]) >= POOL - 1:   # the pinned buffer about to be reused has been delivered (its ticket waited for)
+                c.waitDownload(pending[h].pop(0))
             pending[h].append(c.downloadFrameAsync(pools[h][counts[h] % POOL]))
             counts[h] += 1
-        while len(pending[h]) > POOL - 2:
-            c.waitDownload(pending[h].pop(0))
         return len(sched[i])
 
     def sync_all():
@@ -574,6 +648,8 @@ def main():
         calc.calculateOpticalFlowAsync()
         for b in sched[i]:
             calc.warpFrames(b, hr.BlendedFrame)
+            while len(pending) >= POOL - 1:      # never hand a pinned buffer to a second download before its ticket was waited for
+                calc.waitDownload(pending.pop(0))
             pending.append(calc.downloadFrameAsync(out_pool[dl_count[0] % POOL]))
             dl_count[0] += 1
         while len(pending) > 8:
@@ -589,17 +665,13 @@ def main():
     calc.synchronize()
 
     idx = 0
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()  # sampled from before the warm-up to the end of the end-to-end loops: a short timed region still gets samples
     for _ in range(args.warmup):
         step_device(idx)
         idx += 1
     calc.synchronize()
-    sampler = ClockSampler(local)
-    if rank == 0:
-        sampler.start()
-        for _ in range(args.warmup):  # a little more load while nvidia-smi starts sampling
-            step_device(idx)
-            idx += 1
-        calc.synchronize()
     barrier()
     launches0 = hr.kernel_launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -615,7 +687,6 @@ def main():
     barrier()
     ms = max_over_ranks(e0.elapsed_time(e1))
     launches = sum_over_ranks(hr.kernel_launch_count() - launches0)
-    clocks = sampler.stop() if rank == 0 else None
     total_frames = sum_over_ranks(frames)
     value = total_frames / (ms * 1e-3)
 
@@ -681,10 +752,44 @@ def main():
     e2e_value, mean_out = time_e2e(step_e2e, esteps)
     e2e_blocking_value, _ = time_e2e(step_e2e_blocking, min(args.steps, 30))
 
+    # ---- link roofline of the end-to-end loop: the same bytes per step (1 frame up, N frames down) over the same pinned
+    # buffers on two copy streams, no kernels — what the host link of this box gives all ranks at once ----
+    def link_leg(nsteps):
+        up, down = torch.cuda.Stream(), torch.cuda.Stream()
+        dev_in = torch.empty_like(dev[0])
+        dev_out = torch.empty(out_pinned.numel(), dtype=tdt, device="cuda")
+        n_out = max(1, int(round(mean_out)))
+        for _ in range(2):
+            with torch.cuda.stream(up):
+                dev_in.copy_(pinned[0], non_blocking=True)
+            with torch.cuda.stream(down):
+                out_pool[0].copy_(dev_out, non_blocking=True)
+        torch.cuda.synchronize()
+        barrier()
+        t0 = time.perf_counter()
+        for i in range(nsteps):
+            with torch.cuda.stream(up):
+                dev_in.copy_(pinned[i % RING], non_blocking=True)
+            with torch.cuda.stream(down):
+                for k in range(n_out):
+                    out_pool[(i * n_out + k) % POOL].copy_(dev_out, non_blocking=True)
+        torch.cuda.synchronize()
+        barrier()
+        wall = max_over_ranks((time.perf_counter() - t0) * 1e3) * 1e-3
+        h2d = sum_over_ranks(nsteps * calc.inputFrameBytes) / wall / 1e9
+        d2h = sum_over_ranks(nsteps * n_out * calc.outputFrameBytes) / wall / 1e9
+        return {"h2d_gbs": h2d, "d2h_gbs": d2h, "frames_per_s": sum_over_ranks(nsteps * n_out) / wall, "steps": nsteps,
+                "what": "concurrent pinned H2D (1 frame) + D2H (N frames) per step on two copy streams, no kernels, all ranks at once"}
+
+    link = link_leg(min(args.steps, 50))
+    clocks = sampler.stop() if rank == 0 else None
+
     if rank == 0:
         pk, pk_kind = peaks()
         hbm_peak = float(pk.get("hbm_gbs", 6650.0))
         warp_ms = prof["ms_warp"] / max(prof["n_warp"], 1)
+        blur_ms = max(prof["ms_blur"] / max(prof["n_blur"], 1), 1e-6)
+        pack_ms = max(prof["ms_ingest"] / max(prof["n_ingest"], 1), 1e-6)
         search_ms_per_step = prof["ms_search"] / psteps
         warp_gbs = alg["warp"] / (warp_ms * 1e-3) / 1e9
         sad_peak = None
@@ -703,24 +808,35 @@ def main():
                        "flow_overlap": not args.no_overlap,
                        "mean_outputs_per_source_frame": total_frames / world / args.steps,
                        "realtime_factor_vs_144fps": value / world / 144.0,
-                       "l2": f"ring of {RING} distinct device frames; per-step working set ~{(3*alg['F'] + 2*4*W*H + 6*alg['L']*2 + alg['F'])/1e6:.0f} MB exceeds the 126 MB L2"},
+                       "frames": f"{NFR} distinct frames played back and forth (every consecutive pair is one motion step of the scene)",
+                       "l2": f"inputs larger than L2: {NFR} distinct device frames of {alg['F']/1e6:.0f} MB; a step touches ~{(3*alg['F'] + 2*alg['F'] + 6*(alg['L']*4 + alg['F']))/1e6:.0f} MB (126 MB L2)"},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(calc.inputFrameBytes),
                     "d2h_bytes_per_step": int(round(mean_out * calc.outputFrameBytes)), "steps": esteps,
                     "api": "update_frame (pinned host) + calculate_optical_flow_async + N x (warp_frames + download_frame_async to pinned host) "
                            "+ wait_download; transfers on their own streams overlap the kernels",
-                    "blocking_api_value": e2e_blocking_value},
+                    "blocking_api_value": e2e_blocking_value,
+                    "link": link, "link_peak_frames_per_s": link["frames_per_s"], "frac_of_link": e2e_value / link["frames_per_s"]},
             "gpu_launches": int(launches),
             "clocks": clocks,
-            "roofline": {"kernel": "warpFastKernel = warpFrames (dominant HBM-bound kernel, %d launches/step)" % round(mean_out), "bound": "hbm",
-                         "achieved": warp_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": warp_gbs / hbm_peak,
-                         "traffic": ncu_traffic(args.workload, "warpFastKernel"),
-                         "peak_source": f"{pk_kind} (MEASURED_PEAKS.json hbm_gbs)", "algorithmic_bytes_per_launch": alg["warp"],
-                         "avg_launch_ms": warp_ms},
-            "roofline_search": {"kernel": "search ladder: sadSlideStagedKernel + sadCandKernel, %d passes (dominant by time, integer-ALU bound)" % alg["passes"], "bound": "int_alu",
-                                "achieved": absdiff_rate, "peak": sad_peak, "unit": "G byte-absdiff/s",
-                                "frac": (absdiff_rate / sad_peak) if sad_peak else None,
-                                "peak_source": "hrb_microbench_sad_peak: VABSDIFF4.U8.ACC issue rate measured in this run",
-                                "algorithmic_absdiff_per_step": 3 * args.radius * alg["L"] * alg["passes"], "ms_per_step": search_ms_per_step},
+            # the dominant cost of a step is the search ladder (integer-ALU bound: SURVEY.md section 8d)
+            "roofline": {"kernel": "search ladder: sadTileKernel (windows 8..2048) + sadCandKernel (windows 4, 2), %d passes per source frame" % alg["passes"],
+                         "bound": "int_alu", "achieved": absdiff_rate, "peak": sad_peak, "unit": "G byte-absdiff/s",
+                         "frac": (absdiff_rate / sad_peak) if sad_peak else None,
+                         "traffic": ncu_traffic(args.workload, "search_pass"),
+                         "peak_source": "hrb_microbench_sad_peak: VABSDIFF4.U8.ACC issue rate measured in this run (4 byte-abs-diffs per lane instruction)",
+                         "algorithmic_absdiff_per_step": 3 * args.radius * alg["L"] * alg["passes"], "ms_per_step": search_ms_per_step,
+                         "note": "achieved = 3 * R * L * passes byte-abs-diffs (SURVEY.md section 8d) / CUDA-event time of the ladder; traffic = DRAM bytes per pass (ncu)"},
+            "roofline_warp": {"kernel": "warpFastKernel = warpFrames (HBM-bound, %d launches/step)" % round(mean_out), "bound": "hbm",
+                              "achieved": warp_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": warp_gbs / hbm_peak,
+                              "traffic": ncu_traffic(args.workload, "warpFastKernel"),
+                              "peak_source": f"{pk_kind} (MEASURED_PEAKS.json hbm_gbs)", "algorithmic_bytes_per_launch": alg["warp"],
+                              "avg_launch_ms": warp_ms},
+            "roofline_blur": {"kernel": "blurFlowCellKernel", "bound": "hbm", "achieved": alg["blur"] / (blur_ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
+                              "frac": alg["blur"] / (blur_ms * 1e-3) / 1e9 / hbm_peak, "traffic": ncu_traffic(args.workload, "blurFlowCellKernel"),
+                              "algorithmic_bytes_per_launch": alg["blur"], "avg_launch_ms": blur_ms},
+            "roofline_pack": {"kernel": "packPlanarKernel (ingest: raw frame -> 8-bit search planes)", "bound": "hbm",
+                              "achieved": alg["F"] / (pack_ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s", "frac": alg["F"] / (pack_ms * 1e-3) / 1e9 / hbm_peak,
+                              "traffic": ncu_traffic(args.workload, "packPlanarKernel"), "algorithmic_bytes_per_launch": alg["F"], "avg_launch_ms": pack_ms},
             "search_radius_5": r5,
             "breakdown_ms_per_step": {"ingest": prof["ms_ingest"] / psteps, "search": search_ms_per_step, "blur": prof["ms_blur"] / psteps,
                                       "warp": prof["ms_warp"] / psteps, "kernels_total": step_kernel_ms},
@@ -730,6 +846,9 @@ def main():
                 line["cpu_baseline"] = cpu_baseline(wl)
             except Exception as e:  # noqa: BLE001
                 line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": 0, "kind": "port", "sample": f"failed: {e}"}
+            # the reference's own OpenCL kernels on this same GPU: the like-for-like numbers are
+            # e2e.blocking_api_value vs its value (both blocking APIs) and breakdown_ms_per_step.search vs its ofc_ms
+            line["reference_opencl_b200"] = reference_opencl_same_gpu(wl, radius=args.radius)
         print(json.dumps(line), flush=True)
     calc.close()
     if world > 1:

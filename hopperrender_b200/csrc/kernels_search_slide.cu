@@ -148,23 +148,24 @@ template <int R, int RUN, int PI, typename Fetch> __device__ __forceinline__ voi
 }
 template <int R> __device__ __forceinline__ int chromaShift(int pi, int z) { return ((pi + candOffset<R>(z)) & 1) ? 0 : 1; }
 
-// Staging of a box through the reference's mirror (calcDeltaSumsKernelSDR.h:86-95) without TMA: rows [0, rows) x
-// bytes [c0, c1) of the box; box row r / byte c <-> plane row rb + r / byte ca + c (ca a multiple of 16).  Used for
-// tiles at the frame border and when TMA is off.  PAIRS: chroma plane — columns are mirrored as (U,V) pairs.
-// Every 16-byte chunk is a cp.async copy — all copies of a thread in flight at once, no dependent global load, which
-// would queue behind the staging traffic of the whole grid: rows through the mirrored row index, chunks left / right
-// of the plane from their mirror chunk, which arrives in forward order and is reversed in shared memory afterwards
-// (MirrorBox::fixup, after cpAsyncWaitAll() + a barrier).  Chunks that have no mirror chunk (plane width not a
-// multiple of 16, displacements beyond the frame size) are filled byte by byte in fixup.
-template <bool PAIRS> struct MirrorBox {
-    uint8_t* __restrict__ buf;
-    const uint8_t* __restrict__ plane;
-    int bw, pitch, dimU, dimV, rb, rows, kLo, nK, nCh, pc0;
+// Staging of a box with cp.async, through the reference's mirror (calcDeltaSumsKernelSDR.h:86-95): rows [r0, r1) x
+// the 16-byte chunks [kLo, kLo + nK) of the box; box row r / byte c <-> plane row rb + r / byte ca + c (ca a multiple
+// of 16).  Every chunk is one copy — all copies of a thread in flight at once, and no dependent global load, which
+// would queue behind the staging traffic of the whole grid: rows go through the mirrored row index, chunks left / right
+// of the plane come from their mirror chunk, which arrives in forward order and is reversed in shared memory afterwards
+// (stageFixup, after the copies have landed).  Chunks that have no mirror chunk (plane width not a multiple of 16,
+// displacements beyond the frame size) are filled byte by byte in stageFixup.  One function for the luma box of every
+// tile and for the chroma box wherever TMA does not apply, so that the rarely taken paths run instructions that are
+// already in the instruction cache (a cold path fetches its code through the same congested memory system).
+struct BoxGeom {
+    uint8_t* buf;
+    const uint8_t* plane;
+    int bw, pitch, dimU, dimV, rb, r0, r1, kLo, nK, nCh, pc0;
     bool whole;
-    __device__ __forceinline__ MirrorBox(uint8_t* buf_, int bw_, const uint8_t* plane_, int pitch_, int dimU_, int dimV_, int rb_, int ca, int rows_, int c0, int c1)
-        : buf(buf_), plane(plane_), bw(bw_), pitch(pitch_), dimU(dimU_), dimV(dimV_), rb(rb_), rows(rows_) {
+    __device__ __forceinline__ BoxGeom(uint8_t* buf_, int bw_, const uint8_t* plane_, int pitch_, int dimU_, int dimV_, int rb_, int ca, int r0_, int r1_, int c0, int c1)
+        : buf(buf_), plane(plane_), bw(bw_), pitch(pitch_), dimU(dimU_), dimV(dimV_), rb(rb_), r0(r0_), r1(r1_) {
         kLo = c0 >> 4;
-        nK = ((c1 + 15) >> 4) - kLo;
+        nK = max(((c1 + 15) >> 4) - kLo, 0);
         nCh = dimU >> 4;           // whole chunks of a plane row
         pc0 = (ca >> 4) + kLo;     // plane chunk of box chunk kLo
         whole = (dimU & 15) == 0;
@@ -174,40 +175,46 @@ template <bool PAIRS> struct MirrorBox {
         const int sc = srcChunk(pc);
         return whole ? (sc >= 0 && sc < nCh) : (pc >= 0 && pc < nCh);
     }
-    __device__ __forceinline__ void issue(int tid, int nThreads) const {
+    __device__ __forceinline__ bool outsideChunks() const { return pc0 < 0 || pc0 + nK > nCh; }
+};
+
+__device__ __noinline__ void stageIssue(const BoxGeom g, int tid, int nThreads) {
+    const int n = (g.r1 - g.r0) * g.nK;
 #pragma unroll 1
-        for (int i = tid; i < rows * nK; i += nThreads) {
-            const int r = i / nK, k = i - r * nK;
-            const int pc = pc0 + k;
-            if (direct(pc)) cpAsync16(buf + r * bw + 16 * (kLo + k), rowPtr(plane, pitch, mirrorSearch(rb + r, dimV)) + 16 * srcChunk(pc));
-        }
+    for (int i = tid; i < n; i += nThreads) {
+        const int rr = i / g.nK, k = i - rr * g.nK;
+        const int r = g.r0 + rr, pc = g.pc0 + k;
+        if (g.direct(pc)) cpAsync16(g.buf + r * g.bw + 16 * (g.kLo + k), rowPtr(g.plane, g.pitch, mirrorSearch(g.rb + r, g.dimV)) + 16 * g.srcChunk(pc));
     }
-    __device__ __forceinline__ void fixup(int tid, int nThreads) const {
-        const int nLeft = min(max(-pc0, 0), nK);             // box chunks [0, nLeft) lie left of the plane
-        const int rightStart = min(max(nCh - pc0, 0), nK);   // box chunks [rightStart, nK) lie right of it (or straddle its last column)
-        const int nOut = nLeft + (nK - rightStart);
+}
+
+// pairs: chroma plane — columns are mirrored as (U,V) pairs
+__device__ __noinline__ void stageFixup(const BoxGeom g, bool pairs, int tid, int nThreads) {
+    const int nLeft = min(max(-g.pc0, 0), g.nK);               // box chunks [0, nLeft) lie left of the plane
+    const int rightStart = min(max(g.nCh - g.pc0, 0), g.nK);   // box chunks [rightStart, nK) lie right of it (or straddle its last column)
+    const int nOut = nLeft + (g.nK - rightStart);
+    const int n = (g.r1 - g.r0) * nOut;
 #pragma unroll 1
-        for (int i = tid; i < rows * nOut; i += nThreads) {
-            const int r = i / nOut;
-            int k = i - r * nOut;
-            if (k >= nLeft) k += rightStart - nLeft;
-            const int pc = pc0 + k;
-            uint8_t* __restrict__ d = buf + r * bw + 16 * (kLo + k);
-            if (direct(pc)) {
-                const uint4 w = *reinterpret_cast<const uint4*>(d);
-                const unsigned sel = PAIRS ? 0x1032u : 0x0123u;  // reverse the (U,V) pairs / the bytes of a word
-                *reinterpret_cast<uint4*>(d) = make_uint4(__byte_perm(w.w, 0u, sel), __byte_perm(w.z, 0u, sel), __byte_perm(w.y, 0u, sel), __byte_perm(w.x, 0u, sel));
-            } else {
-                const uint8_t* __restrict__ srcRow = rowPtr(plane, pitch, mirrorSearch(rb + r, dimV));
+    for (int i = tid; i < n; i += nThreads) {
+        const int rr = i / nOut;
+        int k = i - rr * nOut;
+        if (k >= nLeft) k += rightStart - nLeft;
+        const int r = g.r0 + rr, pc = g.pc0 + k;
+        uint8_t* __restrict__ d = g.buf + r * g.bw + 16 * (g.kLo + k);
+        if (g.direct(pc)) {
+            const uint4 w = *reinterpret_cast<const uint4*>(d);
+            const unsigned sel = pairs ? 0x1032u : 0x0123u;  // reverse the (U,V) pairs / the bytes of a word
+            *reinterpret_cast<uint4*>(d) = make_uint4(__byte_perm(w.w, 0u, sel), __byte_perm(w.z, 0u, sel), __byte_perm(w.y, 0u, sel), __byte_perm(w.x, 0u, sel));
+        } else {
+            const uint8_t* __restrict__ srcRow = rowPtr(g.plane, g.pitch, mirrorSearch(g.rb + r, g.dimV));
 #pragma unroll 1
-                for (int j = 0; j < 16; ++j) {
-                    const int vc = 16 * pc + j;
-                    d[j] = __ldg(srcRow + (PAIRS ? 2 * mirrorSearch(vc >> 1, dimU >> 1) + (vc & 1) : mirrorSearch(vc, dimU)));
-                }
+            for (int j = 0; j < 16; ++j) {
+                const int vc = 16 * pc + j;
+                d[j] = __ldg(srcRow + (pairs ? 2 * mirrorSearch(vc >> 1, g.dimU >> 1) + (vc & 1) : mirrorSearch(vc, g.dimU)));
             }
         }
     }
-};
+}
 
 // lean per-layer total: same arithmetic as windowTotal (search_common.cuh), candidate offset given
 __device__ __forceinline__ uint32_t layerTotalOf(const SearchArgs& a, const WindowCtx& c, uint32_t sad, int sq) {
@@ -233,6 +240,7 @@ __global__ void __maxnreg__(128)
     extern __shared__ uint8_t smemRaw[];
     __shared__ uint64_t barY, barC;
     __shared__ int s_rng[4];           // min ou, max ou, min ov, max ov over the windows of the current round
+    __shared__ int s_bb[4];            // bounding box of the round's windows inside the tile: min / max window column, min / max window row
     __shared__ uint32_t s_red[8][16];  // CTA-level sums: [window of the tile][layer] (classes 64 and 128)
     uint8_t* const smem = smemRaw + ((128u - ((unsigned)__cvta_generic_to_shared(smemRaw) & 127u)) & 127u);
     uint8_t* const bufY = smem;
@@ -298,7 +306,6 @@ __global__ void __maxnreg__(128)
         uniOv = View<STEP>::ov(ox, oy);
     }
     const bool manual = !tp.useTma;
-    unsigned phase = 0;
     const int cu = U0 + 4 * lane;
     const bool colOk = cu < vw.lu;   // (lu is a multiple of 4: words are never partial)
 
@@ -309,7 +316,10 @@ __global__ void __maxnreg__(128)
         int minOu = uniOu, maxOu = uniOu, minOv = uniOv, maxOv = uniOv;
         if (C::SPREAD) {
             __syncthreads();  // s_off / s_state of the previous step are visible; nobody reads s_rng or the boxes any more
-            if (tid < 4) s_rng[tid] = (tid & 1) ? INT_MIN : INT_MAX;
+            if (tid < 4) {
+                s_rng[tid] = (tid & 1) ? INT_MIN : INT_MAX;
+                s_bb[tid] = (tid & 1) ? INT_MIN : INT_MAX;
+            }
             __syncthreads();
             {
                 int mn = INT_MAX;
@@ -333,20 +343,25 @@ __global__ void __maxnreg__(128)
             minOv = s_rng[2];
             const int limV = slow ? INT_MAX : minOv + C::SV;
             {
-                int mxU = INT_MIN, mxV = INT_MIN;
+                int mxU = INT_MIN, mxV = INT_MIN, bu0 = INT_MAX, bu1 = INT_MIN, bv0 = INT_MAX, bv1 = INT_MIN;
                 for (int i = tid; i < nwu * nwv; i += NT) {
                     const int ou = (int)(short)(s_off[i] & 0xffff), ov = s_off[i] >> 16;
                     if (s_state[i] == 0 && ou <= limU && ov >= minOv && ov <= limV) {
                         s_state[i] = 1;
                         mxU = max(mxU, ou);
                         mxV = max(mxV, ov);
+                        const int lwu = i % nwu, lwv = i / nwu;
+                        bu0 = min(bu0, lwu); bu1 = max(bu1, lwu); bv0 = min(bv0, lwv); bv1 = max(bv1, lwv);
                     }
                 }
                 mxU = __reduce_max_sync(0xffffffffu, mxU);
                 mxV = __reduce_max_sync(0xffffffffu, mxV);
+                bu0 = __reduce_min_sync(0xffffffffu, bu0); bu1 = __reduce_max_sync(0xffffffffu, bu1);
+                bv0 = __reduce_min_sync(0xffffffffu, bv0); bv1 = __reduce_max_sync(0xffffffffu, bv1);
                 if (lane == 0 && mxU != INT_MIN) {
                     atomicMax(&s_rng[1], mxU);
                     atomicMax(&s_rng[3], mxV);
+                    atomicMin(&s_bb[0], bu0); atomicMax(&s_bb[1], bu1); atomicMin(&s_bb[2], bv0); atomicMax(&s_bb[3], bv1);
                 }
             }
             __syncthreads();
@@ -371,36 +386,46 @@ __global__ void __maxnreg__(128)
         const int colEnd = cbMin - ca + tileCols + (maxOu - minOu) + 4;         // bytes [cbMin - ca, colEnd) of a luma row are read
         const int colEndC = cbMinC - caC + tileCols + ((maxOu & ~1) - (minOu & ~1)) + 2 + 4;
         const bool border = cbMin < 0 || cbMin + tileCols + (maxOu - minOu) + 2 > vw.dimU || rb < 0 || rb + rowsNeeded > vw.dimV;
-        const bool asyncStage = staged && !manual && !border;   // CTA-uniform
-        if (staged && asyncStage) {
+        // rounds after the first stage only the rows and columns their windows can touch (s_bb: bounding box of the round's
+        // windows, in windows of the tile)
+        int subR0 = 0, subR1 = rowsNeeded, subC0 = cbMin - ca, subC1 = min(colEnd, BW), subC0C = cbMinC - caC, subC1C = min(colEndC, BW);
+        if (C::SPREAD && round > 0) {
+            const int t0 = s_bb[2] << WSL, t1 = min((s_bb[3] + 1) << WSL, tileRows);   // tile rows of the round's windows
+            const int u0 = s_bb[0] << WSL, u1 = min((s_bb[1] + 1) << WSL, tileCols);   // tile columns
+            subR0 = t0;
+            subR1 = min(rowsNeeded, t1 + SPAN + (maxOv - minOv));
+            subC0 = cbMin - ca + u0;
+            subC1 = min(cbMin - ca + u1 + (maxOu - minOu) + 4, BW);
+            subC0C = cbMinC - caC + u0;
+            subC1C = min(cbMinC - caC + u1 + ((maxOu & ~1) - (minOu & ~1)) + 2 + 4, BW);
+        }
+        const int subR0C = ((rb + subR0) >> 1) - rbc, subR1C = ((rb + subR1 - 1) >> 1) - rbc + 1;
+        const BoxGeom gy(bufY, BW, vw.y1, vw.pitch, vw.dimU, vw.dimV, rb, ca, subR0, subR1, subC0, subC1);
+        const BoxGeom gc(bufC, BW, vw.c1, vw.pitch, vw.dimU, vw.dimV >> 1, rbc, caC, subR0C, subR1C, subC0C, subC1C);
+        const bool asyncStage = staged && !manual && !border && round == 0;   // CTA-uniform
+        if (asyncStage) {
             // interior tile: the chroma box through the TMA engine (one elected thread), the luma box through the LSU path as
             // 16-byte cp.async copies of all threads — both in flight at once, each completing on its own mbarrier
             if (tid == 0) {
                 mbarExpectTx(&barC, (unsigned)(tp.boxHC * BW));
                 tmaLoad2d(bufC, &mapC, caC, rbc, &barC);
             }
-            const int cpr = (min(colEnd, BW) + 15) >> 4;  // 16-byte chunks of a luma row that are read
-            const uint8_t* __restrict__ src = vw.y1 + ca;
-            for (int i = tid; i < rowsNeeded * cpr; i += NT) {
-                const int r = i / cpr, c = i - r * cpr;
-                cpAsync16(bufY + r * BW + 16 * c, rowPtr(src, vw.pitch, rb + r) + 16 * c);
-            }
+            stageIssue(gy, tid, NT);
             asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"((unsigned)__cvta_generic_to_shared(&barY)) : "memory");
         } else if (staged) {
-            // tile at the frame border (or no TMA): plain loads through the mirror
-            const MirrorBox<true> mc(bufC, BW, vw.c1, vw.pitch, vw.dimU, vw.dimV >> 1, rbc, caC, rowsNeededC, cbMinC - caC, min(colEndC, BW));
-            const MirrorBox<false> my(bufY, BW, vw.y1, vw.pitch, vw.dimU, vw.dimV, rb, ca, rowsNeeded, cbMin - ca, min(colEnd, BW));
-            mc.issue(tid, NT);
-            my.issue(tid, NT);
+            // tile at the frame border, later round, or no TMA: both boxes by cp.async, then the mirror fix-up of the chunks outside the plane
+            stageIssue(gc, tid, NT);
+            stageIssue(gy, tid, NT);
             cpAsyncWaitAll();
             __syncthreads();
-            mc.fixup(tid, NT);
-            my.fixup(tid, NT);
-            __syncthreads();
+            if (gc.outsideChunks() || gy.outsideChunks()) {
+                stageFixup(gc, true, tid, NT);
+                stageFixup(gy, false, tid, NT);
+                __syncthreads();
+            }
         }
         const bool waitTma = asyncStage;
-        const unsigned parity = phase & 1u;   // the barriers complete one phase per asynchronously staged round
-        if (asyncStage) ++phase;
+        const unsigned parity = 0;   // the barriers are used once, by the first round
         bool waitedC = false, waitedY = false;
         if (dbg && tid == 0) {
             if (waitTma) {
@@ -829,7 +854,10 @@ template <int R> int launchTileR(hrb_ofc* h, const SearchArgs& a, int step) { re
 #define HRB_SLIDE_CONCAT(a, b) HRB_SLIDE_CONCAT2(a, b)
 int HRB_SLIDE_CONCAT(launchSearchPassSlidePart, HRB_SLIDE_PART)(hrb_ofc* h, const SearchArgs& a, int R, int step) {
     const int lu = step == 1 ? a.lw : a.lh;
-    if (a.rs != 0 || a.ws < 8 || (lu & 3) != 0) return -1;
+    // windows of 4 and 8 pixels: the tile kernel covers them (variants 2 and 3 run it there, which is how the parity tests reach
+    // those classes), but the staged small-window kernel (kernels_search_cand.cu) is faster on them and is the default
+    const int minWs = h->searchVariant >= 2 ? 4 : 16;
+    if (a.rs != 0 || a.ws < minWs || (lu & 3) != 0) return -1;
     switch (R) {
 #define HRB_CASE(N) case N: return launchTileR<N>(h, a, step);
 #if HRB_SLIDE_PART == 0

@@ -2,4 +2,4 @@
 
 Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may import this.
 """
-from .binding import OracleCalc, RefCalc, kernels, lib_path, num_threads, ref_available, ref_lib_path  # noqa: F401
+from .binding import OracleCalc, RefCalc, kernels, lib_path, num_threads, ref_available, set_num_threads, ref_lib_path  # noqa: F401

@@ -80,6 +80,14 @@ def num_threads():
     return int(_load().orc_num_threads())
 
 
+def set_num_threads(n):
+    """Set the OpenMP thread count of the oracle explicitly (torchrun exports OMP_NUM_THREADS=1)."""
+    lib = _load()
+    lib.orc_set_num_threads.restype = C.c_int
+    lib.orc_set_num_threads.argtypes = [C.c_int]
+    return int(lib.orc_set_num_threads(int(n)))
+
+
 def _p(a):
     assert a.flags["C_CONTIGUOUS"]
     return C.c_void_p(a.ctypes.data)
