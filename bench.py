@@ -450,16 +450,15 @@ def run_streams(args, wl):
         c = calcs[h]
         c.updateFrameDevice(dev[(i + h) % RING])
         c.calculateOpticalFlowAsync()
-        for b in sched[i]:
-            c.warpFrames(b, hr.BlendedFrame)
+        c.warpFramesBatch(sched[i], hr.BlendedFrame)
         return len(sched[i])
 
     def step_e2e(h, i):
         c = calcs[h]
         c.updateFrame(pinned[(i + h) % RING])
         c.calculateOpticalFlowAsync()
+        c.warpFramesBatch(sched[i], hr.BlendedFrame)
         for b in sched[i]:
-            c.warpFrames(b, hr.BlendedFrame)
             while len(pending[h]) >= POOL - 1:   # the pinned buffer about to be reused has been delivered (its ticket waited for)
                 c.waitDownload(pending[h].pop(0))
             pending[h].append(c.downloadFrameAsync(pools[h][counts[h] % POOL]))
@@ -549,6 +548,7 @@ def main():
     ap.add_argument("--workload", default="cfg3", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-overlap", action="store_true", help="keep the asynchronous flow calculation on the compute stream (A/B)")
+    ap.add_argument("--no-batch", action="store_true", help="one warpFrames call per output frame, as the reference's loop does (A/B of warpFramesBatch)")
     ap.add_argument("--radius", type=int, default=SEARCH_RADIUS)
     ap.add_argument("--streams-per-gpu", type=int, default=1, help="independent video streams (handles) per GPU; >1 prints the multi-stream line")
     args = ap.parse_args()
@@ -623,8 +623,11 @@ def main():
     def step_device(i):
         calc.updateFrameDevice(dev[i % RING])
         calc.calculateOpticalFlowAsync()
-        for b in sched[i]:
-            calc.warpFrames(b, hr.BlendedFrame)
+        if args.no_batch:
+            for b in sched[i]:
+                calc.warpFrames(b, hr.BlendedFrame)
+        else:
+            calc.warpFramesBatch(sched[i], hr.BlendedFrame)   # the N output frames of this source frame in one pass
         return len(sched[i])
 
     def step_e2e_blocking(i):
@@ -646,8 +649,11 @@ def main():
         # overlap the kernels; a consumer takes the delivered frames in order, at most ~one source frame behind
         calc.updateFrame(pinned[i % RING])
         calc.calculateOpticalFlowAsync()
+        if not args.no_batch:
+            calc.warpFramesBatch(sched[i], hr.BlendedFrame)
         for b in sched[i]:
-            calc.warpFrames(b, hr.BlendedFrame)
+            if args.no_batch:
+                calc.warpFrames(b, hr.BlendedFrame)
             while len(pending) >= POOL - 1:      # never hand a pinned buffer to a second download before its ticket was waited for
                 calc.waitDownload(pending.pop(0))
             pending.append(calc.downloadFrameAsync(out_pool[dl_count[0] % POOL]))
@@ -791,7 +797,9 @@ def main():
         blur_ms = max(prof["ms_blur"] / max(prof["n_blur"], 1), 1e-6)
         pack_ms = max(prof["ms_ingest"] / max(prof["n_ingest"], 1), 1e-6)
         search_ms_per_step = prof["ms_search"] / psteps
-        warp_gbs = alg["warp"] / (warp_ms * 1e-3) / 1e9
+        n_out_mean = total_frames / world / args.steps
+        warp_bytes = alg["warp"] if args.no_batch else int(2 * alg["F"] + 4 * alg["L"] + n_out_mean * alg["F"])  # batch: sources and flow once, N outputs
+        warp_gbs = warp_bytes / (warp_ms * 1e-3) / 1e9
         sad_peak = None
         try:
             sad_peak = hr.microbench_sad_peak(local)
@@ -826,10 +834,10 @@ def main():
                          "peak_source": "hrb_microbench_sad_peak: VABSDIFF4.U8.ACC issue rate measured in this run (4 byte-abs-diffs per lane instruction)",
                          "algorithmic_absdiff_per_step": 3 * args.radius * alg["L"] * alg["passes"], "ms_per_step": search_ms_per_step,
                          "note": "achieved = 3 * R * L * passes byte-abs-diffs (SURVEY.md section 8d) / CUDA-event time of the ladder; traffic = DRAM bytes per pass (ncu)"},
-            "roofline_warp": {"kernel": "warpFastKernel = warpFrames (HBM-bound, %d launches/step)" % round(mean_out), "bound": "hbm",
+            "roofline_warp": {"kernel": "warpKernel = warpFrames, %s" % ("one launch per output frame" if args.no_batch else "one batched launch per source frame (all its output frames)"), "bound": "hbm",
                               "achieved": warp_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": warp_gbs / hbm_peak,
-                              "traffic": ncu_traffic(args.workload, "warpFastKernel"),
-                              "peak_source": f"{pk_kind} (MEASURED_PEAKS.json hbm_gbs)", "algorithmic_bytes_per_launch": alg["warp"],
+                              "traffic": ncu_traffic(args.workload, "warpKernel"),
+                              "peak_source": f"{pk_kind} (MEASURED_PEAKS.json hbm_gbs)", "algorithmic_bytes_per_launch": warp_bytes,
                               "avg_launch_ms": warp_ms},
             "roofline_blur": {"kernel": "blurFlowCellKernel", "bound": "hbm", "achieved": alg["blur"] / (blur_ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
                               "frac": alg["blur"] / (blur_ms * 1e-3) / 1e9 / hbm_peak, "traffic": ncu_traffic(args.workload, "blurFlowCellKernel"),

@@ -49,6 +49,7 @@ PROTOTYPES = {
     "hrb_ofc_update_frame": (C.c_int, [_P, _P]),
     "hrb_ofc_calculate_optical_flow": (C.c_int, [_P]),
     "hrb_ofc_warp_frames": (C.c_int, [_P, C.c_float, C.c_int]),
+    "hrb_ofc_warp_frames_batch": (C.c_int, [_P, C.c_int, C.POINTER(C.c_float), C.c_int]),
     "hrb_ofc_copy_frame": (C.c_int, [_P]),
     "hrb_ofc_download_frame": (C.c_int, [_P, _P]),
     "hrb_ofc_get_state": (C.c_int, [_P, C.POINTER(hrb_ofc_state)]),

@@ -501,7 +501,6 @@ int hrb_ofc_create(hrb_ofc** out, const hrb_ofc_desc* d) {
     h->tapMode = false;
     h->flowGraphsOn = true;
     h->searchVariant = 0;
-    h->warpVariant = 0;
     h->smCount = 148;
     {
         cudaDeviceProp prop;
@@ -559,7 +558,7 @@ int hrb_ofc_create(hrb_ofc** out, const hrb_ofc_desc* d) {
     const size_t planeBytes = planeYBytes + planeCBytes + 256, planeTBytes = planeYTBytes + planeCTBytes + 256;
     h->levelCapacity = ((lw + 1) / 2) * ((lh + 1) / 2);
     const size_t winSumEntries = ((lw + 63) / 64) * ((lh + 63) / 64) * 16 + 16;
-    const size_t need = 4 * (h->inFrameBytes + planeBytes + planeTBytes) + 3 * h->outFrameBytes + 4 * h->levelCapacity * 2 + winSumEntries * 4 + 3 * 2 * lw * lh * 2;
+    const size_t need = 4 * (h->inFrameBytes + planeBytes + planeTBytes) + hrb_ofc::kOutRing * h->outFrameBytes + 4 * h->levelCapacity * 2 + winSumEntries * 4 + 3 * 2 * lw * lh * 2;
 
     // replaces detectDevices' memory check (opticalFlowCalc.cpp:48-51,86-96)
     size_t freeB = 0, totalB = 0;
@@ -783,9 +782,33 @@ int hrb_ofc_warp_frames(hrb_ofc* h, float blending_scalar, int frame_output_mode
     HRB_REQUIRE(frame_output_mode >= 0 && frame_output_mode <= 6, "frame_output_mode outside 0..6");
     int rc = beginOutput(h);
     if (rc) return rc;
-    rc = launchWarpFrame(h, blending_scalar, frame_output_mode);
+    uint8_t* out = h->outputRing[h->outCur];
+    rc = launchWarpFrames(h, 1, &blending_scalar, &out, frame_output_mode);
     if (rc) return rc;
     HRB_CUDA(cudaEventRecord(h->outReady[h->outCur], h->stream));
+    return HRB_OK;
+}
+
+int hrb_ofc_warp_frames_batch(hrb_ofc* h, int n, const float* blending_scalars, int frame_output_mode) {
+    HRB_REQUIRE(h && blending_scalars, "null argument");
+    HRB_REQUIRE(n >= 1 && n <= HRB_WARP_BATCH_MAX, "batch size outside 1..HRB_WARP_BATCH_MAX");
+    for (int i = 0; i < n; ++i)
+        if (blending_scalars[i] > 1.0f) {  // opticalFlowCalcSDR.cpp:143-146
+            setLastError("[HopperRender] Error in function warpFrames: Blending scalar is greater than 1.0");
+            return HRB_ERR_BLEND_RANGE;
+        }
+    HRB_REQUIRE(frame_output_mode >= 0 && frame_output_mode <= 6, "frame_output_mode outside 0..6");
+    int rc = beginOutput(h);  // waits for the download of the first slot, starts the warp timer
+    if (rc) return rc;
+    uint8_t* outs[HRB_WARP_BATCH_MAX];
+    for (int i = 0; i < n; ++i) {
+        const int slot = (h->outCur + i) % hrb_ofc::kOutRing;
+        if (i) HRB_CUDA(cudaStreamWaitEvent(h->stream, h->outFree[slot], 0));
+        outs[i] = h->outputRing[slot];
+    }
+    rc = launchWarpFrames(h, n, blending_scalars, outs, frame_output_mode);
+    if (rc) return rc;
+    for (int i = 0; i < n; ++i) HRB_CUDA(cudaEventRecord(h->outReady[(h->outCur + i) % hrb_ofc::kOutRing], h->stream));
     return HRB_OK;
 }
 
@@ -1092,7 +1115,6 @@ int hrb_ofc_set_search_variant(hrb_ofc* h, int variant) {
     HRB_REQUIRE(h, "null handle");
     HRB_REQUIRE(variant >= 0 && variant <= 3, "variant must be 0 (automatic), 1 (generic kernels only), 2 (sliding kernel staged without TMA) or 3 (sliding kernel without the aligned fast path)");
     h->searchVariant = variant;
-    h->warpVariant = variant == 1 ? 1 : 0;
     return HRB_OK;
 }
 

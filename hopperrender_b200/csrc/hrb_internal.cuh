@@ -149,7 +149,7 @@ struct hrb_ofc {
     cudaEvent_t flowForkEvent, flowJoinEvent;
     bool flowJoinPending, flowOverlap;
     cudaEvent_t spareFreeEvent;          // compute stream: last readers of the buffer that became input slot [3] are enqueued
-    static constexpr int kOutRing = 3;
+    static constexpr int kOutRing = 2 * HRB_WARP_BATCH_MAX;  // the batch being written plus the previous one still being downloaded
     cudaEvent_t outReady[kOutRing];      // compute stream: warp/copy into ring slot i finished
     cudaEvent_t outFree[kOutRing];       // download stream: D2H of ring slot i finished
     int outCur;                          // ring slot warpFrames / copyFrame write next (advances on download)
@@ -165,7 +165,7 @@ struct hrb_ofc {
     int planePitch;                // bytes per row of the row-major planes
     int planePitchT;               // bytes per row of the transposed planes
     int stripeY0, stripeY1;        // output stripe (luma rows) warpFrames / copyFrame / downloadFrame work on; default the whole frame
-    uint8_t* outputRing[3];        // m_outputFrameArray, as a ring so that a download can overlap the next warp
+    uint8_t* outputRing[kOutRing]; // m_outputFrameArray, as a ring so that downloads overlap the next warps
     int16_t* levelOffsets[2][2];   // [iteration parity][axis] window-level offsets
     size_t levelCapacity;          // entries per level array
     uint32_t* winSums;
@@ -180,7 +180,6 @@ struct hrb_ofc {
 
     // taps / profiling
     int searchVariant;  // 0: automatic kernel selection, 1: generic sadPassKernel for every pass, 2: sliding kernel without TMA, 3: ... without the aligned fast path
-    int warpVariant;    // 0: automatic (table-driven fast kernel for modes 0-2), 1: generic warpFrameKernel for every mode
     int smCount;
     bool tapMode;
     // instantiated CUDA graphs of the flow calculation (search ladder + blur), one per combination of buffers and
@@ -207,7 +206,7 @@ namespace hrb {
 // kernels_frame.cu
 int launchPackFrame(hrb_ofc* h, int slot);
 int launchCopyFrame(hrb_ofc* h, int slot);
-int launchWarpFrame(hrb_ofc* h, float t, int mode);
+int launchWarpFrames(hrb_ofc* h, int n, const float* t, uint8_t* const* out, int mode);
 // kernels_search.cu
 int launchSearchPass(hrb_ofc* h, const SearchArgs& a, int R, int step);
 // kernels_search_slide.cu: HRB_OK, an error code, or -1 when this (R, geometry) is not covered

@@ -105,6 +105,13 @@ class OpticalFlowCalc:
     def warpFrames(self, blendingScalar, frameOutputMode):
         self._check(self._lib.hrb_ofc_warp_frames(self._h, float(blendingScalar), int(frameOutputMode)))
 
+    def warpFramesBatch(self, blendingScalars, frameOutputMode):
+        """The output frames of one source pair in one pass (hrb_ofc_warp_frames_batch): fetch them with len(blendingScalars)
+        downloadFrame / downloadFrameAsync calls."""
+        import ctypes as C
+        arr = (C.c_float * len(blendingScalars))(*[float(b) for b in blendingScalars])
+        self._check(self._lib.hrb_ofc_warp_frames_batch(self._h, len(blendingScalars), arr, int(frameOutputMode)))
+
     def copyFrame(self):
         self._check(self._lib.hrb_ofc_copy_frame(self._h))
 

@@ -112,6 +112,13 @@ HRB_API int hrb_ofc_update_frame(hrb_ofc* h, const uint8_t* input_planes);
 HRB_API int hrb_ofc_calculate_optical_flow(hrb_ofc* h);
 /* warpFrames (opticalFlowCalcSDR.cpp:141-168): asynchronous, result in the device output frame. */
 HRB_API int hrb_ofc_warp_frames(hrb_ofc* h, float blending_scalar, int frame_output_mode);
+/* warpFrames for up to HRB_WARP_BATCH_MAX output frames of the SAME source pair in one pass (beyond the reference, like the
+ * asynchronous calls): output frame i is what hrb_ofc_warp_frames(h, blending_scalars[i], mode) would produce, bit for bit.
+ * The forward / reverse flow of a sample is fetched once for all of them and both source frames cross HBM once.  The n
+ * frames go to consecutive slots of the device output ring; fetch them with n calls of hrb_ofc_download_frame(_async) (in
+ * the order given), with no warp_frames / copy_frame call in between. */
+#define HRB_WARP_BATCH_MAX 8
+HRB_API int hrb_ofc_warp_frames_batch(hrb_ofc* h, int n, const float* blending_scalars, int frame_output_mode);
 /* copyFrame (opticalFlowCalcSDR.cpp:170-183) */
 HRB_API int hrb_ofc_copy_frame(hrb_ofc* h);
 /* downloadFrame (opticalFlowCalcSDR.cpp:31-42): blocking read of 1.5*H*output_stride elements; sets
@@ -128,8 +135,8 @@ HRB_API int hrb_ofc_reset(hrb_ofc* h); /* == hrb_ofc_set_frame_count(h, 0) */
 /* ---- device-resident variants (benchmark / zero-copy callers) ---------------------------------- */
 /* Same as hrb_ofc_update_frame but the source is already in device memory of the handle's GPU. */
 HRB_API int hrb_ofc_update_frame_device(hrb_ofc* h, const void* device_planes);
-/* Device address of the output frame most recently written by warp_frames / copy_frame (one of a ring of three:
- * the slot advances with every download; without downloads it never changes). */
+/* Device address of the output frame most recently written by warp_frames / copy_frame (for a batch: its first frame;
+ * the frames of a batch sit in consecutive slots of a ring that advances with every download). */
 HRB_API int hrb_ofc_output_device_ptr(hrb_ofc* h, void** out);
 /* Asynchronous variants for PINNED host memory.  Transfers run on their own streams: the upload of the next source
  * frame and the downloads of the current outputs overlap the kernels (the output frame is a ring of three on the

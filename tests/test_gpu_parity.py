@@ -88,6 +88,45 @@ def test_warp_modes(synth, hdr, mode, variant, W, H, maxres, inS, outS):
             assert np.array_equal(a2, b2), f"mode {mode} amp {amp} t {t}: {np.count_nonzero(a2 != b2)} differ, max {np.abs(a2 - b2).max()}"
 
 
+@pytest.mark.parametrize("hdr", [False, True])
+@pytest.mark.parametrize("mode", [0, 1, 2, 3, 5])
+@pytest.mark.parametrize("W,H,maxres,outS", [(256, 144, 270, 0), (130, 70, 35, 144), (320, 176, 88, 0)])
+def test_warp_batch_equals_single_calls(synth, hdr, mode, W, H, maxres, outS):
+    """hrb_ofc_warp_frames_batch: frame i of a batch is bit for bit the frame of warpFrames(t[i], mode), and both match the oracle."""
+    g, o = make_pair(hdr, H, W, 0, outS, black=4.0, white=250.0, maxres=maxres)
+    for fr in frames(synth, W, H, hdr, 3):
+        g.updateFrame(fr)
+        o.updateFrame(fr)
+    lh, lw = g.m_opticalFlowFrameHeight, g.m_opticalFlowFrameWidth
+    fl = _smooth_flow(lh, lw, np.random.default_rng(W + mode), 30)
+    g.writeFlow(fl)
+    o.writeFlow(fl)
+    ts = [0.0, 1.0 / 6.0, 2.0 / 6.0, 0.5, 4.0 / 6.0, 5.0 / 6.0, 1.0]
+    g.warpFramesBatch(ts, mode)
+    batch = []
+    for _ in ts:
+        a = out_array(g, hdr)
+        g.downloadFrame(a)
+        batch.append(a)
+    S = outS or W
+    for t, a in zip(ts, batch):
+        g.warpFrames(t, mode)
+        o.warpFrames(t, mode)
+        b, c = out_array(g, hdr), out_array(o, hdr)
+        g.downloadFrame(b)
+        o.downloadFrame(c)
+        a2, b2, c2 = (x.reshape(-1, S)[:, :W].astype(np.int64) for x in (a, b, c))
+        assert np.array_equal(a2, b2), f"t {t}: batch and single call differ in {np.count_nonzero(a2 != b2)} samples"
+        if mode == 3:
+            step = 256 if hdr else 1
+            d = np.abs(a2 - c2)
+            assert d.max() <= step and np.count_nonzero(d) <= max(4, d.size // 500)
+        else:
+            assert np.array_equal(a2, c2), f"t {t}: {np.count_nonzero(a2 != c2)} samples differ from the oracle"
+    with pytest.raises(RuntimeError):
+        g.warpFramesBatch([0.5, 1.5], 2)
+
+
 def test_warp_rejects_blend_above_one(synth):
     g, o = make_pair(False, 48, 64)
     with pytest.raises(RuntimeError):
