@@ -41,6 +41,10 @@ class hrb_ofc_profile(C.Structure):
                 ("n_warp", C.c_uint64), ("n_copy", C.c_uint64)]
 
 
+class hrb_side_data(C.Structure):
+    _fields_ = [("guid", C.c_uint8 * 16), ("data", C.c_void_p), ("bytes", C.c_size_t)]
+
+
 # name -> (restype, argtypes); every symbol include/hrb.h declares
 _P = C.c_void_p
 PROTOTYPES = {
@@ -53,6 +57,7 @@ PROTOTYPES = {
     "hrb_ofc_copy_frame": (C.c_int, [_P]),
     "hrb_ofc_download_frame": (C.c_int, [_P, _P]),
     "hrb_ofc_get_state": (C.c_int, [_P, C.POINTER(hrb_ofc_state)]),
+    "hrb_ofc_peek_state": (C.c_int, [_P, C.POINTER(hrb_ofc_state)]),
     "hrb_ofc_set_params": (C.c_int, [_P, C.POINTER(hrb_ofc_params)]),
     "hrb_ofc_set_frame_count": (C.c_int, [_P, C.c_uint]),
     "hrb_ofc_reset": (C.c_int, [_P]),
@@ -82,6 +87,8 @@ PROTOTYPES = {
     "hrb_ofc_set_search_variant": (C.c_int, [_P, C.c_int]),
     "hrb_ofc_set_flow_overlap": (C.c_int, [_P, C.c_int]),
     "hrb_ofc_join_flow": (C.c_int, [_P]),
+    "hrb_ofc_set_side_data": (C.c_int, [_P, C.POINTER(hrb_side_data), C.c_int]),
+    "hrb_ofc_get_side_data": (C.c_int, [_P, C.POINTER(hrb_side_data), C.c_int, C.POINTER(C.c_int)]),
     "hrb_ofc_debug_timeline": (C.c_int, [_P, C.c_size_t]),
     "hrb_ofc_debug_timeline_read": (C.c_int, [_P, C.c_void_p, C.c_size_t]),
     "hrb_kernel_launch_count": (C.c_uint64, []),

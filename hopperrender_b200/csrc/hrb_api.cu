@@ -896,10 +896,43 @@ int hrb_host_free(void* ptr) {
     return HRB_OK;
 }
 
+// folds in the flow calculations that have FINISHED (oldest first), without waiting for the ones still running
+static int resolveFinishedFlows(hrb_ofc* h) {
+    for (int i = 1; i <= hrb_ofc::kFlowRecords; ++i) {
+        hrb_ofc::FlowRecord& r = h->flowRec[(h->curRec + i) % hrb_ofc::kFlowRecords];
+        if (!r.pending) continue;
+        const cudaError_t q = cudaEventQuery(r.end);
+        if (q == cudaErrorNotReady) {
+            cudaGetLastError();
+            break;  // later records are younger: still running too
+        }
+        HRB_CUDA(q);
+        const int rc = resolveRecord(h, r);
+        if (rc) return rc;
+    }
+    return HRB_OK;
+}
+
+static void fillState(const hrb_ofc* h, hrb_ofc_state* s);
+
+int hrb_ofc_peek_state(hrb_ofc* h, hrb_ofc_state* s) {
+    HRB_REQUIRE(h && s, "null argument");
+    HRB_CUDA(cudaSetDevice(h->device));
+    const int rc = resolveFinishedFlows(h);
+    if (rc) return rc;
+    fillState(h, s);
+    return HRB_OK;
+}
+
 int hrb_ofc_get_state(hrb_ofc* h, hrb_ofc_state* s) {
     HRB_REQUIRE(h && s, "null argument");
     const int rc = resolveFlow(h);
     if (rc) return rc;
+    fillState(h, s);
+    return HRB_OK;
+}
+
+static void fillState(const hrb_ofc* h, hrb_ofc_state* s) {
     s->frame_width = h->frameWidth;
     s->frame_height = h->frameHeight;
     s->input_stride = h->inputStride;
@@ -920,11 +953,14 @@ int hrb_ofc_get_state(hrb_ofc* h, hrb_ofc_state* s) {
     s->neighbor_bias_scalar = h->neighborBiasScalar;
     s->total_frame_delta = h->totalFrameDelta;
     s->frame_count = h->frameCount;
-    return HRB_OK;
 }
 
 int hrb_ofc_set_params(hrb_ofc* h, const hrb_ofc_params* p) {
     HRB_REQUIRE(h && p, "null argument");
+    // the same ranges calculateOpticalFlow accepts (the filter keeps the radius in 5..16, config.h:8-9; 2..4 exist for tests)
+    HRB_REQUIRE(p->search_radius >= 2 && p->search_radius <= 16, "search radius outside 2..16");
+    HRB_REQUIRE(p->delta_scalar >= 0 && p->delta_scalar <= 31 && p->neighbor_bias_scalar >= 0 && p->neighbor_bias_scalar <= 31, "delta/neighbor scalar outside 0..31");
+    HRB_REQUIRE(p->black_level == p->black_level && p->white_level == p->white_level, "levels must be numbers");
     h->searchRadius = p->search_radius;
     h->deltaScalar = p->delta_scalar;
     h->neighborBiasScalar = p->neighbor_bias_scalar;
@@ -1085,6 +1121,32 @@ int hrb_ofc_profile_reset(hrb_ofc* h) {
     for (int i = 0; i < 5; ++i) {
         h->prof.ms[i] = 0;
         h->prof.n[i] = 0;
+    }
+    return HRB_OK;
+}
+
+int hrb_ofc_set_side_data(hrb_ofc* h, const hrb_side_data* items, int count) {
+    HRB_REQUIRE(h && (items || count == 0), "null argument");
+    HRB_REQUIRE(count >= 0 && count <= 64, "side-data count outside 0..64");
+    for (int i = 0; i < count; ++i) HRB_REQUIRE(items[i].data || items[i].bytes == 0, "null blob with a size");
+    h->sideData.clear();
+    h->sideData.resize((size_t)count);
+    for (int i = 0; i < count; ++i) {
+        memcpy(h->sideData[i].guid, items[i].guid, 16);
+        const uint8_t* p = static_cast<const uint8_t*>(items[i].data);
+        h->sideData[i].bytes.assign(p, p + items[i].bytes);
+    }
+    return HRB_OK;
+}
+
+int hrb_ofc_get_side_data(hrb_ofc* h, hrb_side_data* items, int capacity, int* count) {
+    HRB_REQUIRE(h && count, "null argument");
+    HRB_REQUIRE(capacity >= 0 && (items || capacity == 0), "null array with a capacity");
+    *count = (int)h->sideData.size();
+    for (int i = 0; i < capacity && i < *count; ++i) {
+        memcpy(items[i].guid, h->sideData[i].guid, 16);
+        items[i].data = h->sideData[i].bytes.data();
+        items[i].bytes = h->sideData[i].bytes.size();
     }
     return HRB_OK;
 }

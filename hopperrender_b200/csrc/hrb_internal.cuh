@@ -197,6 +197,11 @@ struct hrb_ofc {
     std::vector<hrb::PassTapDev> taps;
     hrb::Profile prof;
     hrb::TmaCache* tmaCache = nullptr;  // TMA descriptors of the search planes, encoded on first use
+    struct SideBlob {
+        uint8_t guid[16];
+        std::vector<uint8_t> bytes;
+    };
+    std::vector<SideBlob> sideData;        // IMediaSideData blobs of the newest source frame (opaque, host memory)
     unsigned long long* dbgDev = nullptr;  // per-CTA timelines of the search passes (debug aid, off by default)
     size_t dbgStride = 0;                  // words per pass
 };

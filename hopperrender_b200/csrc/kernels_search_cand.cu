@@ -283,10 +283,11 @@ template <int R, int STEP, bool TAPS, int WS> __global__ void __launch_bounds__(
 }
 
 template <int R, int STEP, bool TAPS, int WS> int launchCandOne(hrb_ofc* h, const SearchArgs& a) {
-    static bool configured[HRB_MAX_DEVICES] = {};  // the attribute is per device
-    if (!configured[h->device & (HRB_MAX_DEVICES - 1)]) {
+    static std::atomic<bool> configured[HRB_MAX_DEVICES];  // the attribute is per device; handles may be created on several host threads
+    std::atomic<bool>& cfg = configured[h->device & (HRB_MAX_DEVICES - 1)];
+    if (!cfg.load(std::memory_order_acquire)) {
         HRB_CUDA(cudaFuncSetAttribute(sadCandKernel<R, STEP, TAPS, WS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)candSmem<WS>()));
-        configured[h->device & (HRB_MAX_DEVICES - 1)] = true;
+        cfg.store(true, std::memory_order_release);
     }
     const int lu = STEP == 1 ? a.lw : a.lh, lv = STEP == 1 ? a.lh : a.lw;
     const dim3 grid((lu + CT_U - 1) / CT_U, (lv + CT_V - 1) / CT_V, 1);

@@ -55,6 +55,7 @@ class OpticalFlowCalc:
                            whiteLevel, maxCalcRes, 1 if self._is_hdr else 0, device, stream)
         self._check(self._lib.hrb_ofc_create(C.byref(self._h), C.byref(d)))
         s = self._state()
+        self._geom = s  # geometry never changes on a live object: read it once (every later field access would be a round trip)
         self._in_bytes = (s.frame_height * s.input_stride + (s.frame_height // 2) * s.input_stride) * (2 if self._is_hdr else 1)
         self._out_bytes = (s.frame_height * s.output_stride + (s.frame_height // 2) * s.output_stride) * (2 if self._is_hdr else 1)
 
@@ -68,8 +69,14 @@ class OpticalFlowCalc:
         self._check(self._lib.hrb_ofc_get_state(self._h, C.byref(s)))
         return s
 
+    def _peek(self):
+        """Public fields without waiting for flow calculations still in flight (hrb_ofc_peek_state)."""
+        s = L.hrb_ofc_state()
+        self._check(self._lib.hrb_ofc_peek_state(self._h, C.byref(s)))
+        return s
+
     def _set(self, **kw):
-        s = self._state()
+        s = self._peek()  # the live parameters are host-side values: no need to wait for the GPU
         p = L.hrb_ofc_params(s.search_radius, s.delta_scalar, s.neighbor_bias_scalar, s.output_black_level, s.output_white_level)
         for k, v in kw.items():
             setattr(p, k, v)
@@ -154,13 +161,13 @@ class OpticalFlowCalc:
         return p.value or 0
 
     # ---- public fields (opticalFlowCalc.h:26-50) ---------------------------------------------------
-    m_frameWidth = property(lambda s: s._state().frame_width)
-    m_frameHeight = property(lambda s: s._state().frame_height)
-    m_inputStride = property(lambda s: s._state().input_stride)
-    m_outputStride = property(lambda s: s._state().output_stride)
-    m_opticalFlowResScalar = property(lambda s: s._state().res_scalar)
-    m_opticalFlowFrameWidth = property(lambda s: s._state().flow_width)
-    m_opticalFlowFrameHeight = property(lambda s: s._state().flow_height)
+    m_frameWidth = property(lambda s: getattr(s._geom, 'frame_width'))
+    m_frameHeight = property(lambda s: getattr(s._geom, 'frame_height'))
+    m_inputStride = property(lambda s: getattr(s._geom, 'input_stride'))
+    m_outputStride = property(lambda s: getattr(s._geom, 'output_stride'))
+    m_opticalFlowResScalar = property(lambda s: getattr(s._geom, 'res_scalar'))
+    m_opticalFlowFrameWidth = property(lambda s: getattr(s._geom, 'flow_width'))
+    m_opticalFlowFrameHeight = property(lambda s: getattr(s._geom, 'flow_height'))
     m_ofcCalcTime = property(lambda s: s._state().ofc_calc_time)
     m_ofcAvgCalcTime = property(lambda s: s._state().ofc_avg_calc_time)
     m_ofcPeakCalcTime = property(lambda s: s._state().ofc_peak_calc_time)
@@ -171,7 +178,7 @@ class OpticalFlowCalc:
 
     @property
     def m_frameCount(self):
-        return self._state().frame_count
+        return self._peek().frame_count
 
     @m_frameCount.setter
     def m_frameCount(self, v):  # the filter writes 0 on seek, HopperRender.cpp:840
@@ -179,7 +186,7 @@ class OpticalFlowCalc:
 
     @property
     def m_opticalFlowSearchRadius(self):
-        return self._state().search_radius
+        return self._peek().search_radius
 
     @m_opticalFlowSearchRadius.setter
     def m_opticalFlowSearchRadius(self, v):  # HopperRender.cpp:1448,1457
@@ -187,7 +194,7 @@ class OpticalFlowCalc:
 
     @property
     def m_deltaScalar(self):
-        return self._state().delta_scalar
+        return self._peek().delta_scalar
 
     @m_deltaScalar.setter
     def m_deltaScalar(self, v):  # HopperRender.cpp:1386
@@ -195,7 +202,7 @@ class OpticalFlowCalc:
 
     @property
     def m_neighborBiasScalar(self):
-        return self._state().neighbor_bias_scalar
+        return self._peek().neighbor_bias_scalar
 
     @m_neighborBiasScalar.setter
     def m_neighborBiasScalar(self, v):  # HopperRender.cpp:1387
@@ -203,7 +210,7 @@ class OpticalFlowCalc:
 
     @property
     def m_outputBlackLevel(self):
-        return self._state().output_black_level
+        return self._peek().output_black_level
 
     @m_outputBlackLevel.setter
     def m_outputBlackLevel(self, v):  # HopperRender.cpp:1388
@@ -211,7 +218,7 @@ class OpticalFlowCalc:
 
     @property
     def m_outputWhiteLevel(self):
-        return self._state().output_white_level
+        return self._peek().output_white_level
 
     @m_outputWhiteLevel.setter
     def m_outputWhiteLevel(self, v):  # HopperRender.cpp:1389
@@ -283,6 +290,27 @@ class OpticalFlowCalc:
     # ---- measurement ----------------------------------------------------------------------------------
     def setSearchVariant(self, variant):
         self._check(self._lib.hrb_ofc_set_search_variant(self._h, int(variant)))
+
+    def setSideData(self, blobs):
+        """Attach the IMediaSideData blobs {guid (16 bytes): bytes} of the frame given to the last updateFrame (hrb_ofc_set_side_data)."""
+        items = (L.hrb_side_data * max(len(blobs), 1))()
+        keep = []
+        for i, (guid, data) in enumerate(blobs.items()):
+            assert len(guid) == 16
+            items[i].guid[:] = list(guid)
+            buf = C.create_string_buffer(bytes(data), len(data))
+            keep.append(buf)
+            items[i].data = C.cast(buf, C.c_void_p)
+            items[i].bytes = len(data)
+        self._check(self._lib.hrb_ofc_set_side_data(self._h, items, len(blobs)))
+
+    def getSideData(self):
+        """The blobs that belong to the output frames being delivered (hrb_ofc_get_side_data), as {guid: bytes}."""
+        n = C.c_int(0)
+        self._check(self._lib.hrb_ofc_get_side_data(self._h, None, 0, C.byref(n)))
+        items = (L.hrb_side_data * max(n.value, 1))()
+        self._check(self._lib.hrb_ofc_get_side_data(self._h, items, n.value, C.byref(n)))
+        return {bytes(items[i].guid): C.string_at(items[i].data, items[i].bytes) if items[i].bytes else b"" for i in range(n.value)}
 
     def debugTimeline(self, words_per_pass):
         """Debug aid: per-CTA timelines of the tile search kernels of the following flow calculations (0 = off)."""

@@ -78,6 +78,9 @@ class DeliveryLoop:
         self.iPeakSceneChangeDelta = 0
         self.iPeakSceneChangeDelta2 = 0
         self.log = []
+        # True: the output frames of a source frame come from ONE warpFramesBatch pass (hrb_ofc_warp_frames_batch) instead of one
+        # warpFrames call each; the delivered frames are the same.  Needs a calculator that has the batched entry point.
+        self.batch = False
 
     @property
     def active(self):
@@ -209,10 +212,22 @@ class DeliveryLoop:
             self.frameDeltaHistory.append((fc, c.m_totalFrameDelta))
             while self.frameDeltaHistory and (fc - self.frameDeltaHistory[0][0]) > frames_in_3s:
                 self.frameDeltaHistory.popleft()
+        batched = False
         for i in range(n_int):
             scene_change = self._scene_change()
             warped = self.active and c.m_frameCount >= 3 and not scene_change
-            if warped:
+            if warped and self.batch and i == 0 and n_int <= 8:
+                # the scene-change decision depends on the delta history only: it is the same for every output frame of this
+                # source frame, so all of them are warped, at the blend scalars the loop below steps through
+                blends, b = [], self.dBlendingScalar
+                for _ in range(n_int):
+                    blends.append(b)
+                    b = advance_blend(b, self.rtTargetFrameTime, self.rtCurrPlaybackFrameTime)
+                c.warpFramesBatch(blends, self.iFrameOutput)
+                batched = True
+            if warped and batched:
+                pass  # frame i of the batch is the next one downloadFrame fetches
+            elif warped:
                 c.warpFrames(self.dBlendingScalar, self.iFrameOutput)
             else:
                 c.copyFrame()

@@ -126,7 +126,11 @@ HRB_API int hrb_ofc_copy_frame(hrb_ofc* h);
 HRB_API int hrb_ofc_download_frame(hrb_ofc* h, uint8_t* output_planes);
 
 /* ---- public fields ----------------------------------------------------------------------------- */
+/* get_state waits for every flow calculation in flight (total_frame_delta and the calc-time statistics are those of the
+ * newest one); peek_state never blocks: it reflects the calculations that have finished so far.  A caller that polls
+ * fields between calculate_optical_flow_async and the warps uses peek_state so that host and GPU keep overlapping. */
 HRB_API int hrb_ofc_get_state(hrb_ofc* h, hrb_ofc_state* out);
+HRB_API int hrb_ofc_peek_state(hrb_ofc* h, hrb_ofc_state* out);
 HRB_API int hrb_ofc_set_params(hrb_ofc* h, const hrb_ofc_params* p);
 /* m_frameCount = n; the filter writes 0 on seek (HopperRender.cpp:840) */
 HRB_API int hrb_ofc_set_frame_count(hrb_ofc* h, unsigned int n);
@@ -143,7 +147,8 @@ HRB_API int hrb_ofc_output_device_ptr(hrb_ofc* h, void** out);
  * device, the upload has its own input slot).
  *   update_frame_async : the buffer must stay untouched until hrb_ofc_wait_upload (or synchronize) returns.
  *   download_frame_async: hands out a ticket; the buffer is valid after hrb_ofc_wait_download(ticket) (tickets may be
- *                         waited for in any order; only the 16 most recent ones are tracked, older ones have completed). */
+ *                         waited for in any order: a wait on an old ticket waits for the newest download that reuses its slot (tickets share 16
+ *                         event slots), which proves the old copy has landed — it never returns early). */
 HRB_API int hrb_ofc_update_frame_async(hrb_ofc* h, const uint8_t* pinned_input_planes);
 HRB_API int hrb_ofc_wait_upload(hrb_ofc* h);
 HRB_API int hrb_ofc_download_frame_async(hrb_ofc* h, uint8_t* pinned_output_planes, unsigned long long* ticket);
@@ -158,6 +163,21 @@ HRB_API int hrb_host_register(void* ptr, size_t bytes);
 HRB_API int hrb_host_unregister(void* ptr);
 HRB_API int hrb_host_alloc(void** out, size_t bytes);
 HRB_API int hrb_host_free(void* ptr);
+
+/* ---- side data of the source frames ----------------------------------------------------------------------------- */
+/* The filter reads the IMediaSideData blobs of the input sample (HDR10 / HDR10+ / Dolby Vision metadata and RPU, control
+ * flags, content light level, EIA-608 captions, 3D offset: HopperRender.cpp:875-900) and sets them on EVERY output sample it
+ * delivers for that source frame (:993-1022).  The library keeps them beside the frame: set_side_data attaches copies of
+ * `count` blobs to the frame given to the LAST update_frame call (count 0 clears); get_side_data returns the blobs of that
+ * frame for the output frames being delivered.  The pointers stay valid until the next set_side_data or destroy.  The
+ * contents are opaque to the library. */
+typedef struct hrb_side_data {
+    uint8_t guid[16];   /* the interface id the blob was read with (IMediaSideData.h) */
+    const void* data;
+    size_t bytes;
+} hrb_side_data;
+HRB_API int hrb_ofc_set_side_data(hrb_ofc* h, const hrb_side_data* items, int count);
+HRB_API int hrb_ofc_get_side_data(hrb_ofc* h, hrb_side_data* items, int capacity, int* count);
 
 /* ---- spatial split of one stream over several GPUs ----------------------------------------------------------- */
 /* Restrict warp_frames / copy_frame / download_frame to the luma rows [row_begin, row_end) (even bounds) and the
