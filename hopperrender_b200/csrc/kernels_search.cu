@@ -22,7 +22,7 @@ namespace {
 // flow pixels in (u, v) coordinates (see View); a warp owns 4 consecutive v, a lane one u.  R is compile-time
 // so the candidate displacements fold into the address arithmetic.
 // ------------------------------------------------------------------------------------------------
-template <int R, int STEP> __global__ void __launch_bounds__(256) sadPassKernel(const SearchArgs a) {
+template <int R, int STEP, bool WIDE> __global__ void __launch_bounds__(256) sadPassKernel(const SearchArgs a) {
     __shared__ uint32_t s_sums[16][16];  // [window inside the tile][layer]
     const View<STEP> vw(a);
     const int lane = threadIdx.x, warp = threadIdx.y;
@@ -53,19 +53,28 @@ template <int R, int STEP> __global__ void __launch_bounds__(256) sadPassKernel(
             const int su = cu << a.rs;
             const int ou = View<STEP>::ou(ox, oy), ov = View<STEP>::ov(ox, oy);
             const int fu = mirrorSearch(su + ou, vw.dimU);  // frame-1 column of this lane
-            for (int r = 0; r < gh; ++r) {
-                const int cv = cv0 + r;
-                if (cv >= vw.lv) break;
+            // WIDE (flow fields of a few hundred tiles at most): the rows of the group are independent; unrolled, the loads of all
+            // of them are in flight together — a pass over so few tiles is bound by the latency of its dependent loads, not by
+            // their number.  Larger fields keep the rolled loop (fewer registers, more resident warps).
+#pragma unroll(WIDE ? 4 : 1)
+            for (int r = 0; r < 4; ++r) {
+                const int cv = min(cv0 + r, vw.lv - 1);
+                const bool rowOk = r < gh && cv0 + r < vw.lv;
                 const int sv = cv << a.rs;
                 const uint32_t f2 = fetchPixel(vw.y2, vw.c2, vw.pitch, sv, su);
                 const int bv = sv + ov;
                 if (bv + LO >= 0 && bv + HI < vw.dimV) {
 #pragma unroll
-                    for (int z = 0; z < R; ++z) acc[z] = sad4(fetchPixel(vw.y1, vw.c1, vw.pitch, bv + candOffset<R>(z), fu), f2, acc[z]);
+                    for (int z = 0; z < R; ++z) {
+                        const uint32_t s = sad4(fetchPixel(vw.y1, vw.c1, vw.pitch, bv + candOffset<R>(z), fu), f2, 0u);
+                        if (rowOk) acc[z] += s;
+                    }
                 } else {
 #pragma unroll
-                    for (int z = 0; z < R; ++z)
-                        acc[z] = sad4(fetchPixel(vw.y1, vw.c1, vw.pitch, mirrorSearch(bv + candOffset<R>(z), vw.dimV), fu), f2, acc[z]);
+                    for (int z = 0; z < R; ++z) {
+                        const uint32_t s = sad4(fetchPixel(vw.y1, vw.c1, vw.pitch, mirrorSearch(bv + candOffset<R>(z), vw.dimV), fu), f2, 0u);
+                        if (rowOk) acc[z] += s;
+                    }
                 }
             }
         }
@@ -182,10 +191,18 @@ template <int R> int launchPassR(hrb_ofc* h, const SearchArgs& a, int step, unsi
     }
     if (!done) {
         // generic kernel; windows larger than its tile are finalized by the last CTA of each window
-        if (step == 0)
-            sadPassKernel<R, 0><<<grid, block, 0, h->stream>>>(a);
-        else
-            sadPassKernel<R, 1><<<grid, block, 0, h->stream>>>(a);
+        const bool wide = grid.x * grid.y <= 2u * (unsigned)h->smCount;
+        if (step == 0) {
+            if (wide)
+                sadPassKernel<R, 0, true><<<grid, block, 0, h->stream>>>(a);
+            else
+                sadPassKernel<R, 0, false><<<grid, block, 0, h->stream>>>(a);
+        } else {
+            if (wide)
+                sadPassKernel<R, 1, true><<<grid, block, 0, h->stream>>>(a);
+            else
+                sadPassKernel<R, 1, false><<<grid, block, 0, h->stream>>>(a);
+        }
         HRB_LAUNCH_CHECK();
     }
     *launches = 1;
