@@ -238,7 +238,7 @@ __global__ void __maxnreg__(128)
     constexpr int RUN = C::RUN, BW = C::BW, BWW = C::BWW;
     constexpr int WSL = WSC < 128 ? ilog2c(WSC) : 0;  // log2 of the window size for the classes below 128
     extern __shared__ uint8_t smemRaw[];
-    __shared__ uint64_t barY, barC;
+    __shared__ uint64_t barY, barC, barC2;
     __shared__ int s_rng[4];           // min ou, max ou, min ov, max ov over the windows of the current round
     __shared__ int s_bb[4];            // bounding box of the round's windows inside the tile: min / max window column, min / max window row
     __shared__ uint32_t s_red[8][16];  // CTA-level sums: [window of the tile][layer] (classes 64 and 128)
@@ -269,6 +269,7 @@ __global__ void __maxnreg__(128)
     if (tid == 0) {
         mbarInit(&barY, NT);  // every thread arrives once its own cp.async copies of the luma box have landed
         mbarInit(&barC, 1);   // the elected thread arrives with the byte count of the chroma TMA box
+        mbarInit(&barC2, NT); // ... or every thread, where the chroma box is staged by cp.async too
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         if (dbg) {
             unsigned smid;
@@ -402,8 +403,11 @@ __global__ void __maxnreg__(128)
         const int subR0C = ((rb + subR0) >> 1) - rbc, subR1C = ((rb + subR1 - 1) >> 1) - rbc + 1;
         const BoxGeom gy(bufY, BW, vw.y1, vw.pitch, vw.dimU, vw.dimV, rb, ca, subR0, subR1, subC0, subC1);
         const BoxGeom gc(bufC, BW, vw.c1, vw.pitch, vw.dimU, vw.dimV >> 1, rbc, caC, subR0C, subR1C, subC0C, subC1C);
-        const bool asyncStage = staged && !manual && !border && round == 0;   // CTA-uniform
-        if (asyncStage) {
+        const bool needFix = gc.outsideChunks() || gy.outsideChunks();                  // chunks left / right of the plane: reversed after landing
+        const bool tmaStage = staged && !manual && !border && round == 0;               // CTA-uniform, like the two below
+        const bool pipeStage = staged && round == 0 && !tmaStage && !needFix;
+        const bool asyncStage = tmaStage || pipeStage;
+        if (tmaStage) {
             // interior tile: the chroma box through the TMA engine (one elected thread), the luma box through the LSU path as
             // 16-byte cp.async copies of all threads — both in flight at once, each completing on its own mbarrier
             if (tid == 0) {
@@ -412,24 +416,32 @@ __global__ void __maxnreg__(128)
             }
             stageIssue(gy, tid, NT);
             asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"((unsigned)__cvta_generic_to_shared(&barY)) : "memory");
+        } else if (pipeStage) {
+            // tile at the top / bottom border (rows come through the mirrored row index) or no TMA: both boxes by cp.async, each on
+            // its own mbarrier, so that the chroma of a run is worked on while the luma box is still landing
+            stageIssue(gc, tid, NT);
+            asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"((unsigned)__cvta_generic_to_shared(&barC2)) : "memory");
+            stageIssue(gy, tid, NT);
+            asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"((unsigned)__cvta_generic_to_shared(&barY)) : "memory");
         } else if (staged) {
-            // tile at the frame border, later round, or no TMA: both boxes by cp.async, then the mirror fix-up of the chunks outside the plane
+            // left / right border or a later round: both boxes by cp.async, then the mirror fix-up of the chunks outside the plane
             stageIssue(gc, tid, NT);
             stageIssue(gy, tid, NT);
             cpAsyncWaitAll();
             __syncthreads();
-            if (gc.outsideChunks() || gy.outsideChunks()) {
+            if (needFix) {
                 stageFixup(gc, true, tid, NT);
                 stageFixup(gy, false, tid, NT);
                 __syncthreads();
             }
         }
         const bool waitTma = asyncStage;
+        uint64_t* const barChroma = tmaStage ? &barC : &barC2;
         const unsigned parity = 0;   // the barriers are used once, by the first round
         bool waitedC = false, waitedY = false;
         if (dbg && tid == 0) {
             if (waitTma) {
-                mbarWait(&barC, parity);
+                mbarWait(barChroma, parity);
                 mbarWait(&barY, parity);
                 waitedC = waitedY = true;
             }
@@ -479,7 +491,7 @@ __global__ void __maxnreg__(128)
                 for (int z = 0; z < 16; ++z) accC[z] = 0;
                 // chroma: one pass (ou even) or two passes 2 bytes apart (ou odd)
                 if (waitTma && !waitedC) {
-                    mbarWait(&barC, parity);
+                    mbarWait(barChroma, parity);
                     waitedC = true;
                 }
                 {
@@ -516,7 +528,7 @@ __global__ void __maxnreg__(128)
             } else if (runOk && staged) {
                 // partial run at the last rows of the flow field: compact loops, one (row, candidate) at a time
                 if (waitTma && !waitedC) {
-                    mbarWait(&barC, parity);
+                    mbarWait(barChroma, parity);
                     waitedC = true;
                 }
                 if (waitTma && !waitedY) {

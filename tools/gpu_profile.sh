@@ -8,15 +8,15 @@ mkdir -p gpurun_out/prof
 BENCH="python bench.py --workload $WL --steps 2 --warmup 3 --no-cpu-baseline"
 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -s 200 -c 300 --csv --log-file gpurun_out/prof/launches_$TAG.csv $BENCH > gpurun_out/prof/launches_$TAG.out 2>&1
 echo "launch list rc=$?"
-K='regex:packFrameKernel|sadSlide|sadCandKernel|sadPassKernel|finalizeLarge|blurFlow|warpFastKernel|warpFrameKernel'
+K='regex:packPlanarKernel|sadTileKernel|sadCandKernel|sadPassKernel|blurFlow|warpKernel|copyFrameKernel'
 # skip the priming uploads (3 pack kernels) and four whole steps, then take a bit more than one step
-timeout 1500 ncu --set full --clock-control none --import-source on -k "$K" -s 123 -c 34 -f -o /tmp/prof_step_$TAG $BENCH > gpurun_out/prof/ncu_step_$TAG.out 2>&1
+timeout 1500 ncu --set full --clock-control none --import-source on -k "$K" -s 100 -c 30 -f -o /tmp/prof_step_$TAG $BENCH > gpurun_out/prof/ncu_step_$TAG.out 2>&1
 echo "step capture rc=$?"
 f=/tmp/prof_step_$TAG.ncu-rep
 if [ -f $f ]; then
   ls -la $f
   ncu -i $f --page raw --csv > gpurun_out/prof/step_raw_$TAG.csv 2>/dev/null
-  sz=$(stat -c %s $f)
-  if [ $sz -lt 40000000 ]; then cp $f gpurun_out/prof/; fi
+  ncu -i $f --page source --csv > /tmp/step_source_$TAG.csv 2>/dev/null
+  python tools/sass_hist.py /tmp/step_source_$TAG.csv 1 14 > gpurun_out/prof/sass_weighted_tile_$TAG.txt 2>&1
 fi
 ls -la gpurun_out/prof | tail -5

@@ -84,7 +84,7 @@ def step(tag, out, workload):
     idx = {h: i for i, h in enumerate(hdr)}
     names = [short(d[idx["Kernel Name"]]) for d in data]
     # one step = from a packFrameKernel to the next
-    packs = [i for i, n in enumerate(names) if "packFrame" in n]
+    packs = [i for i, n in enumerate(names) if "packPlanar" in n or "packFrame" in n]
     a, b = (packs[0], packs[1]) if len(packs) > 1 else (0, len(data))
     sel = list(range(a, b))
 
@@ -122,9 +122,10 @@ def step(tag, out, workload):
         tot_us += val(i, "gpu__time_duration.sum")
         out.write(f"| {i - a} | `{names[i][:48]}` | " + " | ".join(cells) + f" | {rd:.1f} | {wr:.1f} |\n")
         key = names[i].split("<")[0]
-        t = traffic.setdefault(key, [0, 0.0])
-        t[0] += 1
-        t[1] += (rd + wr) * 1e6
+        for kk in ([key] + (["search_pass"] if key.startswith("sad") else [])):   # search_pass: every pass kernel of the ladder together
+            t = traffic.setdefault(kk, [0, 0.0])
+            t[0] += 1
+            t[1] += (rd + wr) * 1e6
     out.write(f"\nSum of the step's kernel durations under ncu (cold caches, serialised): {tot_us:.0f} us.\n\n")
     tj = os.path.join(ROOT, "profiles", "ncu_traffic.json")
     try:
