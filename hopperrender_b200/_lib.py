@@ -99,7 +99,7 @@ PROTOTYPES = {
 
 HRB_OK, HRB_ERR_INVALID_ARG, HRB_ERR_CUDA, HRB_ERR_BLEND_RANGE, HRB_ERR_NO_DEVICE, HRB_ERR_STATE = range(6)
 TAP_WINDOW_SUMS, TAP_WINDOW_LAYER, TAP_OFFSETS = 0, 1, 2
-BUF_OFFSET_ARRAY, BUF_FLOW_FOR_WARP, BUF_FLOW_LATEST, BUF_OUTPUT_FRAME, BUF_RAW_FRAME_DELTA = range(5)
+BUF_OFFSET_ARRAY, BUF_FLOW_FOR_WARP, BUF_FLOW_LATEST, BUF_OUTPUT_FRAME, BUF_RAW_FRAME_DELTA, BUF_FLOW_PEAK = range(6)
 
 _lib = None
 

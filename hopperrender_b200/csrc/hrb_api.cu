@@ -1060,6 +1060,10 @@ int hrb_ofc_read_buffer(hrb_ofc* h, int which, void* dst, size_t bytes) {
     } else if (which == HRB_BUF_RAW_FRAME_DELTA) {
         HRB_REQUIRE(bytes == sizeof(uint32_t), "size must be 4");
         HRB_CUDA(cudaMemcpyAsync(dst, h->rawDeltaDev, bytes, cudaMemcpyDeviceToHost, h->stream));
+    } else if (which == HRB_BUF_FLOW_PEAK) {
+        HRB_REQUIRE(bytes == 2 * sizeof(uint32_t), "size must be 8");
+        for (int i = 0; i < 2; ++i)
+            HRB_CUDA(cudaMemcpyAsync(static_cast<uint32_t*>(dst) + i, h->flowMaxDev[i], sizeof(uint32_t), cudaMemcpyDeviceToHost, h->stream));
     } else {
         HRB_REQUIRE(false, "unknown buffer");
     }

@@ -278,6 +278,12 @@ class OpticalFlowCalc:
         self._check(self._lib.hrb_ofc_read_buffer(self._h, L.BUF_FLOW_LATEST if latest else L.BUF_FLOW_FOR_WARP, _ptr(a), a.nbytes))
         return a
 
+    def readFlowPeak(self):
+        """(peak |flow| of the field warpFrames reads, of the latest field): the bound the warp kernel uses to skip the mirror."""
+        a = np.zeros(2, np.uint32)
+        self._check(self._lib.hrb_ofc_read_buffer(self._h, L.BUF_FLOW_PEAK, _ptr(a), a.nbytes))
+        return int(a[0]), int(a[1])
+
     def writeFlow(self, flow, latest=False):
         flow = np.ascontiguousarray(flow, np.int16)
         self._check(self._lib.hrb_ofc_write_flow(self._h, L.BUF_FLOW_LATEST if latest else L.BUF_FLOW_FOR_WARP, _ptr(flow), flow.size))

@@ -203,7 +203,8 @@ enum {
     HRB_BUF_FLOW_FOR_WARP = 1,    /* int16 [2][flow_h][flow_w]: m_blurredOffsetArray[0] (what warpFrames reads) */
     HRB_BUF_FLOW_LATEST = 2,      /* int16 [2][flow_h][flow_w]: m_blurredOffsetArray[1] (result of the last calculate) */
     HRB_BUF_OUTPUT_FRAME = 3,     /* m_outputFrameArray */
-    HRB_BUF_RAW_FRAME_DELTA = 4   /* uint32: the raw window sum total_frame_delta is derived from */
+    HRB_BUF_RAW_FRAME_DELTA = 4,  /* uint32: the raw window sum total_frame_delta is derived from */
+    HRB_BUF_FLOW_PEAK = 5         /* uint32 [2]: max |value| of the flow warpFrames reads, and of the latest one (the bound the warp kernel uses to skip the mirror) */
 };
 HRB_API int hrb_ofc_read_buffer(hrb_ofc* h, int which, void* dst, size_t bytes);
 /* overwrite a blurred flow (HRB_BUF_FLOW_FOR_WARP / HRB_BUF_FLOW_LATEST) — lets tests drive warp_frames */
