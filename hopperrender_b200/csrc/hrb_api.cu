@@ -176,6 +176,7 @@ static int issueFlowKernels(hrb_ofc* h, int R, int ws0, int iterations, bool iss
             a.tapSums = nullptr;
             a.tapLayer = nullptr;
             a.dbg = h->dbgDev ? h->dbgDev + (size_t)(iter * 2 + step) * h->dbgStride : nullptr;
+            a.winLanes = h->searchVariant != 4;
             if (h->tapMode) {
                 PassTapDev t;
                 t.g.windowSize = ws;
@@ -1179,7 +1180,7 @@ int hrb_ofc_join_flow(hrb_ofc* h) {
 
 int hrb_ofc_set_search_variant(hrb_ofc* h, int variant) {
     HRB_REQUIRE(h, "null handle");
-    HRB_REQUIRE(variant >= 0 && variant <= 3, "variant must be 0 (automatic), 1 (generic kernels only), 2 (sliding kernel staged without TMA) or 3 (sliding kernel without the aligned fast path)");
+    HRB_REQUIRE(variant >= 0 && variant <= 4, "variant must be 0 (automatic), 1 (generic kernel only), 2 (tile kernel without TMA), 3 (tile kernel, per-pixel path forced) or 4 (butterfly form for windows of 2 and 4)");
     h->searchVariant = variant;
     return HRB_OK;
 }

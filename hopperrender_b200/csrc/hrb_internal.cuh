@@ -77,6 +77,7 @@ struct SearchArgs {
     uint32_t* tapSums;     // optional [R][nWy][nWx]
     uint8_t* tapLayer;     // optional [nWy][nWx]
     unsigned long long* dbg;  // optional per-CTA timeline of this pass (hrb_ofc_debug_timeline): 8 words per CTA
+    bool winLanes;         // windows of 2 and 4: one lane per window (off: search variant 4, the butterfly form, for A/B runs)
 };
 
 // The search representation of one input slot: 8-bit planes in both orientations, one allocation.

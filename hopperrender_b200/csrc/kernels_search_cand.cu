@@ -170,6 +170,117 @@ __device__ __forceinline__ void candGroups(const SearchArgs& a, const View<STEP>
     }
 }
 
+// Frame-2 samples of one window of 2 or 4 as they lie in the planes: WS luma rows (2 or 4 bytes each) and the WS/2 chroma
+// rows under them.  Loaded one window ahead of the arithmetic (the first one before the tile is staged).
+template <int WS> struct RawWindow {
+    uint32_t y[WS], c[WS / 2];
+};
+template <int STEP, int WS> __device__ __forceinline__ RawWindow<WS> loadRawWindow(const View<STEP>& vw, int cu, int cv) {
+    RawWindow<WS> w;
+#pragma unroll
+    for (int r = 0; r < WS; ++r) {
+        const uint8_t* p = rowPtr(vw.y2, vw.pitch, cv + r) + cu;
+        w.y[r] = WS == 2 ? (uint32_t)__ldg(reinterpret_cast<const uint16_t*>(p)) : __ldg(reinterpret_cast<const uint32_t*>(p));
+    }
+#pragma unroll
+    for (int r = 0; r < WS / 2; ++r) {
+        const uint8_t* p = rowPtr(vw.c2, vw.pitch, (cv >> 1) + r) + cu;
+        w.c[r] = WS == 2 ? (uint32_t)__ldg(reinterpret_cast<const uint16_t*>(p)) : __ldg(reinterpret_cast<const uint32_t*>(p));
+    }
+    return w;
+}
+// window (column wl, row k of the warp's group `it`) of lane `lane` in warp `warp`: first pixel inside the tile
+template <int WS> __device__ __forceinline__ void winOfLane(int lane, int warp, int it, int& wl, int& lwv) {
+    constexpr int NWU = CT_U / WS, ROWS = 32 / NWU;
+    wl = lane & (NWU - 1);
+    lwv = (warp * 16) / WS + it * ROWS + lane / NWU;
+}
+
+// Windows of 2 or 4 flow pixels on a tile that needs no range checks: ONE LANE OWNS ONE WINDOW.  Its R sums stay in the
+// lane's registers from the first SAD to the arg-min — no butterfly between lanes, the window's context (offsets of the
+// four neighbours) is loaded once, and the arg-min needs no shuffle.  A warp covers 16 x 2 (ws = 2) or 8 x 4 (ws = 4)
+// windows of its 16 tile rows.  Lanes of window row k visit the window's columns rotated by k, which spreads the 32
+// lanes of one LDS over 32 banks (the window rows lie a multiple of 8 words apart).
+template <int R, int STEP, bool TAPS, int WS>
+__device__ __forceinline__ void winGroups(const SearchArgs& a, const View<STEP>& vw, const CandTile& t, int lane, int warp, RawWindow<WS> ahead) {
+    constexpr int LO = candOffset<R>(0);
+    constexpr int L2 = WS == 2 ? 1 : 2;
+    constexpr int NWU = CT_U >> L2;          // windows across the tile: 16 / 8
+    constexpr int ROWS = 32 / NWU;           // window rows a warp covers at once: 2 / 4
+    constexpr int NIT = 16 / (ROWS * WS);    // iterations over the warp's 16 tile rows: 4 / 1
+    const int k = lane / NWU;
+#pragma unroll 1
+    for (int it = 0; it < NIT; ++it) {
+        int wl, lwv;  // window column / row inside the tile
+        winOfLane<WS>(lane, warp, it, wl, lwv);
+        const int cu = t.U0 + wl * WS, cv = t.V0 + lwv * WS;
+        const RawWindow<WS> raw = ahead;
+        if (it + 1 < NIT && cu < vw.lu && cv + ROWS * WS < vw.lv) ahead = loadRawWindow<STEP, WS>(vw, cu, cv + ROWS * WS);
+        if (cu >= vw.lu || cv >= vw.lv) continue;  // tile at the end of the field: the window does not exist (windows are whole here)
+        const int wu = cu >> L2, wv = cv >> L2;
+        const int wx = View<STEP>::wx(wu, wv), wy = View<STEP>::wy(wu, wv);
+        const int packed = t.s_off[lwv * NWU + wl];
+        const int ou = (int)(short)(packed & 0xffff), ov = packed >> 16;
+        const int ox = STEP == 1 ? ou : ov, oy = STEP == 1 ? ov : ou;
+        const uint32_t* __restrict__ q = &t.s_f1[(cv - t.V0 + ov - t.minOv) * SP + (wl * WS + ou - t.minOu + t.sh)];
+
+        // frame-2 pixels of the window as {Y, U, V, 0} words, columns in this lane's rotated order
+        uint32_t f2[WS][WS];
+        const uint32_t* qc[WS];
+        if (WS == 2) {
+            const uint32_t y0 = raw.y[0], y1 = raw.y[1], uv = raw.c[0];
+            const uint32_t selA = k ? 0x7541u : 0x7540u, selB = k ? 0x7540u : 0x7541u;  // {Y_c, U, V, 0}
+            f2[0][0] = __byte_perm(y0, uv, selA); f2[0][1] = __byte_perm(y0, uv, selB);
+            f2[1][0] = __byte_perm(y1, uv, selA); f2[1][1] = __byte_perm(y1, uv, selB);
+            qc[0] = q + k; qc[1] = q + (k ^ 1);
+        } else {
+            const uint32_t rot = k == 0 ? 0x3210u : k == 1 ? 0x0321u : k == 2 ? 0x1032u : 0x2103u;  // bytes rotated right by k
+#pragma unroll
+            for (int rr = 0; rr < 2; ++rr) {
+                const uint32_t cw = raw.c[rr];
+                const uint32_t cA = __byte_perm(cw, 0u, 0x4104), cB = __byte_perm(cw, 0u, 0x4324);  // {0, U, V, 0} of columns 0-1 / 2-3
+#pragma unroll
+                for (int r = 2 * rr; r < 2 * rr + 2; ++r) {
+                    const uint32_t yw = __byte_perm(raw.y[r], 0u, rot);
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) f2[r][j] = __byte_perm(yw, (((j + k) & 3) >> 1) ? cB : cA, 0x7650 + j);
+                }
+            }
+#pragma unroll
+            for (int j = 0; j < 4; ++j) qc[j] = q + ((j + k) & 3);
+        }
+
+        uint32_t acc[16];
+#pragma unroll
+        for (int z = 0; z < 16; ++z) acc[z] = 0;
+#pragma unroll
+        for (int r = 0; r < WS; ++r)
+#pragma unroll
+            for (int z = 0; z < R; ++z)
+#pragma unroll
+                for (int j = 0; j < WS; ++j) acc[z] = sad4(qc[j][(r + candOffset<R>(z) - LO) * SP], f2[r][j], acc[z]);
+
+        const WindowCtx c = loadWindowCtx<STEP>(a, wx, wy, ox, oy);
+        uint32_t bestT = 0xffffffffu;
+        int bestZ = 0;  // no layer beats a sum of 2^32-1: layer 0 stands, as with the reference's strict <
+#pragma unroll
+        for (int z = 0; z < R; ++z) {
+            const uint32_t total = layerTotal(a, c, acc[z], candOffset<R>(z));
+            if (TAPS) tapTotal<R>(a, wx, wy, z, total);
+            if (total < bestT) {
+                bestT = total;
+                bestZ = z;
+            }
+        }
+        const int16_t nOff = (int16_t)(c.o + signedSquare(bestZ - R / 2));
+        if (STEP == 0)
+            a.curX[wy * a.nWx + wx] = nOff;
+        else
+            a.curY[wy * a.nWx + wx] = nOff;
+        if (TAPS && a.tapLayer) a.tapLayer[wy * a.nWx + wx] = (uint8_t)bestZ;
+    }
+}
+
 template <int R, int STEP, bool TAPS, int WS> __global__ void __launch_bounds__(256, 4) sadCandKernel(const SearchArgs a) {
     constexpr int LO = candOffset<R>(0), HI = candOffset<R>(R - 1), SPAN = HI - LO;
     constexpr int wsLog2 = WS == 2 ? 1 : WS == 4 ? 2 : WS == 8 ? 3 : WS == 16 ? 4 : 5;
@@ -184,6 +295,18 @@ template <int R, int STEP, bool TAPS, int WS> __global__ void __launch_bounds__(
     const int lane = threadIdx.x, warp = threadIdx.y;
     const int tid = warp * 32 + lane;
     const int U0 = blockIdx.x * CT_U, V0 = blockIdx.y * CT_V;
+
+    // windows of 2 and 4 on a full tile: frame-2 samples of the lane's first window, in flight while the tile is staged
+    constexpr int WSW = WS <= 4 ? WS : 2;
+    const bool fullTile = U0 + CT_U <= vw.lu && V0 + CT_V <= vw.lv;
+    // one lane per window wherever the tile holds whole windows only
+    const bool winTile = WS <= 4 && a.winLanes && (fullTile || (vw.lu % WSW == 0 && vw.lv % WSW == 0));
+    RawWindow<WSW> ahead = {};
+    if (winTile) {
+        int wl, lwv;
+        winOfLane<WSW>(lane, warp, 0, wl, lwv);
+        if (U0 + wl * WSW < vw.lu && V0 + lwv * WSW < vw.lv) ahead = loadRawWindow<STEP, WSW>(vw, U0 + wl * WSW, V0 + lwv * WSW);
+    }
 
     // ---- A. offsets of the tile's windows, and their range ------------------------------------------------------
     if (tid < 4) s_rng[tid] = (tid & 1) ? INT_MIN : INT_MAX;
@@ -227,8 +350,10 @@ template <int R, int STEP, bool TAPS, int WS> __global__ void __launch_bounds__(
     const int sh = cb - ca;
     const int rb = V0 + minOv + LO;       // first row any candidate reads
     if (staged) {
-        const bool interior = ca >= 0 && ca + SP <= vw.pitch && cb + RU <= vw.dimU && rb >= 0 && rb + RV <= vw.dimV;
-        if (interior) {
+        // columns inside the frame: whole rows are copied, rows beyond the top / bottom edge through the mirror
+        // (calcDeltaSumsKernelSDR.h:86-95 reflects each coordinate on its own)
+        const bool colsInside = ca >= 0 && ca + SP <= vw.pitch && cb + RU <= vw.dimU;
+        if (colsInside) {
             // the region is assembled from the planes: one luma word and one chroma word give four {Y,U,V,0} words
             // (expand4); four rows per iteration keep eight loads of a thread in flight
             const int c4 = tid & 15;
@@ -239,9 +364,9 @@ template <int R, int STEP, bool TAPS, int WS> __global__ void __launch_bounds__(
                     uint32_t yw[4], cw[4];
 #pragma unroll
                     for (int i = 0; i < 4; ++i) {
-                        const int rr = min(r + 16 * i, RV - 1);
-                        yw[i] = __ldg(reinterpret_cast<const uint32_t*>(rowPtr(ysrc, vw.pitch, rb + rr)));
-                        cw[i] = __ldg(reinterpret_cast<const uint32_t*>(rowPtr(csrc, vw.pitch, (rb + rr) >> 1)));
+                        const int mr = mirrorSearch(rb + min(r + 16 * i, RV - 1), vw.dimV);
+                        yw[i] = __ldg(reinterpret_cast<const uint32_t*>(rowPtr(ysrc, vw.pitch, mr)));
+                        cw[i] = __ldg(reinterpret_cast<const uint32_t*>(rowPtr(csrc, vw.pitch, mr >> 1)));
                     }
 #pragma unroll
                     for (int i = 0; i < 4; ++i) {
@@ -267,7 +392,9 @@ template <int R, int STEP, bool TAPS, int WS> __global__ void __launch_bounds__(
     CandTile t;
     t.s_f1 = s_f1; t.s_sums = s_sums; t.s_off = s_off;
     t.U0 = U0; t.V0 = V0; t.minOu = minOu; t.minOv = minOv; t.sh = sh; t.staged = staged;
-    if (staged && U0 + CT_U <= vw.lu && V0 + CT_V <= vw.lv)
+    if (staged && winTile)
+        winGroups<R, STEP, TAPS, WSW>(a, vw, t, lane, warp, ahead);
+    else if (staged && fullTile)
         candGroups<R, STEP, TAPS, WS, true>(a, vw, t, lane, warp);
     else
         candGroups<R, STEP, TAPS, WS, false>(a, vw, t, lane, warp);

@@ -219,9 +219,10 @@ typedef struct hrb_ofc_profile {
 HRB_API int hrb_ofc_set_profile(hrb_ofc* h, int on);
 HRB_API int hrb_ofc_profile_read(hrb_ofc* h, hrb_ofc_profile* out); /* synchronizes */
 HRB_API int hrb_ofc_profile_reset(hrb_ofc* h);
-/* Kernel selection (search ladder and warp): 0 = automatic (specialised kernels where they apply), 1 = the generic
- * kernels for every pass and every warp, 2 = like 0 but the L1-fed sliding kernel, 3 = like 0 but the persistent,
- * double-buffered sliding kernel.
+/* Kernel selection for the search ladder: 0 = automatic (tile kernel for windows >= 16, staged small-window kernel
+ * below), 1 = the generic kernel for every pass, 2 = tile kernel without TMA (cp.async staging only) and down to
+ * windows of 4, 3 = like 2 with the per-pixel fallback forced for every window, 4 = like 0 but windows of 2 and 4 use the
+ * lane-per-pixel-column form with a butterfly reduction instead of one lane per window.
  * Results are identical; exists for A/B measurements and parity tests. */
 HRB_API int hrb_ofc_set_search_variant(hrb_ofc* h, int variant);
 /* hrb_ofc_calculate_optical_flow_async runs the search on its own stream, beside the warps issued after it (they read

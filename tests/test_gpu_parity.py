@@ -159,7 +159,7 @@ SEARCH_CASES = [
 ]
 
 
-@pytest.mark.parametrize("variant", [0, 1, 2, 3], ids=["auto", "generic", "l1slide", "pipelined"])
+@pytest.mark.parametrize("variant", [0, 1, 2, 3, 4], ids=["auto", "generic", "notma", "perpixel", "butterfly"])
 @pytest.mark.parametrize("hdr,W,H,maxres,inS,R,kind", SEARCH_CASES)
 def test_search_ladder_taps(synth, hdr, W, H, maxres, inS, R, kind, variant):
     """Every pass of the ladder: window sums, arg-min layers and offsets are bit-exact — with the automatic kernel
