@@ -225,7 +225,28 @@ def cpu_step_runner(wl, rows):
     return step
 
 
+class _StdoutToStderr:
+    """The reference's host classes print to stdout (opticalFlowCalc.cpp:104-107); the bench's stdout carries ONE JSON line, so
+    while they run file descriptor 1 points at stderr."""
+    def __enter__(self):
+        sys.stdout.flush()
+        self._saved = os.dup(1)
+        os.dup2(2, 1)
+        return self
+
+    def __exit__(self, *exc):
+        sys.stdout.flush()
+        os.dup2(self._saved, 1)
+        os.close(self._saved)
+        return False
+
+
 def reference_opencl_same_gpu(wl, steps=8, radius=SEARCH_RADIUS):
+    with _StdoutToStderr():
+        return _reference_opencl_same_gpu(wl, steps, radius)
+
+
+def _reference_opencl_same_gpu(wl, steps, radius):
     """The reference ITSELF — unmodified HopperRender host classes + OpenCL kernel strings (oracle/_ref) — through the NVIDIA
     OpenCL driver on this box's GPU, with the filter's call sequence, its blocking transfers and its own event timers
     (opticalFlowCalcSDR.cpp:119-138, :32-41).  None when oracle/_ref is not built or no OpenCL device accepts it."""

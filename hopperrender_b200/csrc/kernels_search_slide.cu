@@ -1,5 +1,6 @@
-// kernels_search_slide.cu — search passes for windows of 4x4 flow pixels and larger at full flow resolution
-// (20 of the 22 passes at 4K).  Same arithmetic as sadPassKernel (kernels_search.cu), different data movement.
+// kernels_search_slide.cu — the tile kernel: search passes for windows of 16 flow pixels and larger at full flow
+// resolution (16 of the 22 passes at 4K; down to windows of 4 under search variant 2).  Same arithmetic as sadPassKernel
+// (kernels_search.cu), different data movement.
 //
 // Data: the 8-bit planar search planes (luma + NV12-style chroma, see SearchArgs), so one VABSDIFF4 covers FOUR
 // luma pixels, or the U,V samples of four pixels, instead of one pixel, and the two frames of a pass are 25 MB —
@@ -8,13 +9,17 @@
 // Work split (u = contiguous axis, v = candidate axis, see View): a CTA owns a tile of 128 (u) x 32*NWV (v) flow
 // pixels; a warp owns 128 x 32 of it, a lane a column of 4 pixels (one word), which it walks in runs of
 // RUN = min(ws, 32) rows (one window row per run).
-//   * frame 1: ONE luma box and ONE chroma box per tile hold every sample any candidate of any window of the tile can
+//   * frame 1: one luma box and one chroma box per tile hold every sample any candidate of any window of the tile can
 //     touch: tile + candidate span + the spread of the tile's window displacements (motion fields are smooth: a few
-//     pixels).  They are staged by TMA (cp.async.bulk.tensor.2d issued by one elected thread, completion on an
-//     mbarrier); the box starts at the 16-byte boundary below the smallest displaced column (TMA needs that
-//     alignment), each lane re-aligns its words with one funnel shift per sample.  Boxes that leave the frame come
-//     back zero-filled there; the CTA patches those bytes through the reference's mirror
-//     (calcDeltaSumsKernelSDR.h:86-95).  Tiles whose displacements spread beyond the box take a per-pixel path.
+//     pixels).  The chroma box is one TMA copy (cp.async.bulk.tensor.2d issued by one elected thread, completion by
+//     transaction count on an mbarrier); the luma rows are 144-160 bytes wide, where 16-byte cp.async copies issued by
+//     all threads (arriving on a second mbarrier, cp.async.mbarrier.arrive.noinc) measured faster than a TMA box.  Boxes
+//     start at the 16-byte boundary below the smallest displaced column (TMA needs that alignment); each lane re-aligns
+//     its words with one funnel shift per sample.  Tiles whose boxes leave the frame are staged by cp.async through the
+//     reference's mirror (calcDeltaSumsKernelSDR.h:86-95): mirrored ROW indices for the top / bottom edge, byte-reversed
+//     16-byte chunks for the left / right edge (stageIssue / stageFixup).
+//   * windows of a tile whose displacements differ by more than the box allows are handled in up to MAX_ROUNDS rounds
+//     (each round stages the box of one group of windows); what is still left takes a per-pixel path.
 //   * along v every lane slides over its staged column: each frame-1 sample is fetched ONCE and feeds every
 //     (row, candidate) pair it belongs to (up to R of them), all register indices being compile-time.
 //   * chroma: the U,V pair of luma (v, u) is c[v >> 1][u & ~1].  Along v, luma rows 2k and 2k+1 with displacement s

@@ -9,7 +9,7 @@ HRB_REF_BUDGET_S=40 timeout 900 python bench.py --impl reference --steps 2 --war
 for wl in cfg1 cfg2; do
   timeout 600 python bench.py --workload $wl --steps 400 --warmup 5 --no-cpu-baseline > $O/bench_${wl}_$TAG.json 2> $O/bench_${wl}_$TAG.err; echo "$wl rc=$?"
 done
-for s in 2 4 8; do
+for s in 8; do
   timeout 600 python bench.py --streams-per-gpu $s --steps 100 --warmup 5 > $O/bench_streams${s}_$TAG.json 2> $O/bench_streams${s}_$TAG.err; echo "streams $s rc=$?"
 done
 timeout 900 python bench.py --workload cfg4 --steps 20 --warmup 3 > $O/bench_cfg4_n1_$TAG.json 2> $O/bench_cfg4_n1_$TAG.err; echo "cfg4 rc=$?"
