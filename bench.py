@@ -102,7 +102,7 @@ class ClockSampler:
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "20"],
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", os.environ.get("HRB_CLOCK_MS", "20")],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._pump, daemon=True)
             self.thread.start()
@@ -141,6 +141,8 @@ class ClockSampler:
 def bind_near_gpu(local):
     """Pin this process to the CPU cores (and so, by first touch, its pinned buffers to the memory) next to its GPU.
     Matters for the end-to-end numbers at N>1: eight ranks on one NUMA node share that node's memory bandwidth."""
+    if os.environ.get("HRB_NO_BIND"):
+        return None
     try:
         import pynvml
         pynvml.nvmlInit()

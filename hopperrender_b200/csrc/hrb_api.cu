@@ -361,9 +361,9 @@ static int finishUpdate(hrb_ofc* h) {
     // every reader of the buffer that just became slot [3] (the warps of the previous source frame) is already enqueued
     HRB_CUDA(cudaEventRecord(h->spareFreeEvent, h->stream));
     // an asynchronous flow still in flight reads the search planes of slots [1] and [2] as they were when it was
-    // enqueued; three updates later the ingest writes one of them.  Order the ingest behind it (free in steady state:
-    // the next calculate joins anyway).
-    if (h->flowJoinPending) HRB_CUDA(cudaStreamWaitEvent(h->stream, h->flowJoinEvent, 0));
+    // enqueued; the third update after it writes one of them and is ordered behind it.  The first two do not touch
+    // them, so in the usual update / calculate alternation the ingest of frame N+1 runs beside the search of frame N.
+    if (h->flowJoinPending && ++h->updatesSinceFlow >= 3) HRB_CUDA(cudaStreamWaitEvent(h->stream, h->flowJoinEvent, 0));
     return launchPackFrame(h, 2);
 }
 
@@ -762,6 +762,7 @@ int hrb_ofc_calculate_optical_flow_async(hrb_ofc* h) {
     if (rc) return rc;
     HRB_CUDA(cudaEventRecord(h->flowJoinEvent, h->flowStream));
     h->flowJoinPending = true;
+    h->updatesSinceFlow = 0;
     return HRB_OK;
 }
 

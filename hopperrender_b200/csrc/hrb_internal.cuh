@@ -149,6 +149,7 @@ struct hrb_ofc {
     cudaStream_t flowStream;             // asynchronous flow calculations run here, beside the warps of the same source frame
     cudaEvent_t flowForkEvent, flowJoinEvent;
     bool flowJoinPending, flowOverlap;
+    int updatesSinceFlow = 0;      // update_frame calls since the flow in flight was enqueued (see finishUpdate)
     cudaEvent_t spareFreeEvent;          // compute stream: last readers of the buffer that became input slot [3] are enqueued
     static constexpr int kOutRing = 2 * HRB_WARP_BATCH_MAX;  // the batch being written plus the previous one still being downloaded
     cudaEvent_t outReady[kOutRing];      // compute stream: warp/copy into ring slot i finished
