@@ -417,6 +417,7 @@ def run_split(args, wl):
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": int(s.stripe_bytes()),
                     "d2h_bytes_per_step": int(round(frames / args.steps * s.stripe_bytes())), "note": "bytes per rank"},
             "gpu_launches": int(launches),
+            "host_issue_ms_per_step": host_issue_ms,
         }
         print(json.dumps(line), flush=True)
     s.close()
@@ -705,11 +706,15 @@ def main():
     launches0 = hr.kernel_launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     frames = 0
+    host_issue_ms = None
     with torch.cuda.stream(stream):
         e0.record(stream)
-        for _ in range(args.steps):
+        th = time.perf_counter()
+        for k in range(args.steps):
             frames += step_device(idx)
             idx += 1
+            if k == 31:  # host time to ISSUE a step, taken before the launch queue can push back (the GPU is far behind here)
+                host_issue_ms = (time.perf_counter() - th) * 1e3 / 32
         calc.joinFlow()  # the last flow runs on the handle's flow stream: the end event waits for it too
         e1.record(stream)
     calc.synchronize()

@@ -19,7 +19,7 @@ for i in range(2 * len(order)):
     h.updateFrameDevice(dev[order[i % len(order)]])
     h.calculateOpticalFlowAsync()
     h.warpFramesBatch(sched[i], hr.BlendedFrame)
-    if i >= 4:
+    if i >= 0:
         h.synchronize()
         pk = h.readFlowPeak()
         fw = np.abs(h.readFlow(latest=False).astype(np.int32))

@@ -144,7 +144,7 @@ def main():
     os.makedirs(os.path.join(ROOT, "profiles"), exist_ok=True)
     dst = os.path.join(ROOT, "profiles", f"ncu_summary_{tag}.md")
     with open(dst, "w") as out:
-        out.write(f"# ncu summary {tag} ({workload})\n\nCommand: `python bench.py --workload {workload} --steps 2 --warmup 3 --no-cpu-baseline` under ncu "
+        out.write(f"# ncu summary {tag} ({workload})\n\nCommands: `python bench.py --workload {workload} --steps 2 --warmup 3 --no-cpu-baseline` (launch list) and `... --steps 4 --warmup 6 ...` with the first seven steps skipped (`--set full` capture of one steady-state step) under ncu "
                   "(tools/gpu_profile.sh); numbers taken under the profiler are for SHARES and per-kernel counters only, never bench values.\n\n")
         launches(tag, out)
         step(tag, out, workload)
