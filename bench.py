@@ -417,7 +417,6 @@ def run_split(args, wl):
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": int(s.stripe_bytes()),
                     "d2h_bytes_per_step": int(round(frames / args.steps * s.stripe_bytes())), "note": "bytes per rank"},
             "gpu_launches": int(launches),
-            "host_issue_ms_per_step": host_issue_ms,
         }
         print(json.dumps(line), flush=True)
     s.close()
@@ -853,6 +852,7 @@ def main():
                     "blocking_api_value": e2e_blocking_value,
                     "link": link, "link_peak_frames_per_s": link["frames_per_s"], "frac_of_link": e2e_value / link["frames_per_s"]},
             "gpu_launches": int(launches),
+            "host_issue_ms_per_step": host_issue_ms,
             "clocks": clocks,
             # the dominant cost of a step is the search ladder (integer-ALU bound: SURVEY.md section 8d)
             "roofline": {"kernel": "search ladder: sadTileKernel (windows 8..2048) + sadCandKernel (windows 4, 2), %d passes per source frame" % alg["passes"],
