@@ -643,9 +643,13 @@ def main():
         return shard.combine(v, 0.0)[0]
 
     # ---- device-resident loop ---------------------------------------------------------------------
+    dbg_peak = bool(os.environ.get("HRB_DEBUG_PEAK"))
+
     def step_device(i):
         calc.updateFrameDevice(dev[i % RING])
         calc.calculateOpticalFlowAsync()
+        if dbg_peak and i < 10:  # diagnostics: the flow peak the warp kernel is about to read (synchronizes)
+            print(f"step {i}: flow peak (for warp, latest) {calc.readFlowPeak()} t {[round(float(b), 4) for b in sched[i]]}", file=sys.stderr)
         if args.no_batch:
             for b in sched[i]:
                 calc.warpFrames(b, hr.BlendedFrame)

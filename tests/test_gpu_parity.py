@@ -89,6 +89,36 @@ def test_warp_modes(synth, hdr, mode, variant, W, H, maxres, inS, outS):
 
 
 @pytest.mark.parametrize("hdr", [False, True])
+@pytest.mark.parametrize("mode", [0, 1, 2])
+def test_warp_flow_outliers_beyond_the_tables(synth, hdr, mode):
+    """A smooth flow with a few outliers of 150-300 pixels on a frame large enough for interior items: the lean warp items
+    check their own displacements, items that hold an outlier (directly or through the displaced reverse-flow lookup) take
+    the general path, and the batch equals the oracle frame by frame."""
+    W, H = 1280, 960
+    g, o = make_pair(hdr, H, W, 0, 0, black=2.0, white=252.0, maxres=H)
+    for fr in frames(synth, W, H, hdr, 3, None):
+        g.updateFrame(fr)
+        o.updateFrame(fr)
+    lh, lw = g.m_opticalFlowFrameHeight, g.m_opticalFlowFrameWidth
+    assert (lh, lw) == (H, W)
+    rng = np.random.default_rng(77 + mode)
+    fl = _smooth_flow(lh, lw, rng, 12)
+    for k in range(40):  # isolated outliers and small patches, both axes, both signs, also near the frame edge
+        y, x = int(rng.integers(0, lh - 8)), int(rng.integers(0, lw - 8))
+        fl[int(rng.integers(0, 2)), y:y + int(rng.integers(1, 8)), x:x + int(rng.integers(1, 8))] = int(rng.choice([-300, -180, -150, 150, 200, 300]))
+    g.writeFlow(fl)
+    o.writeFlow(fl)
+    ts = [0.0, 1.0 / 6.0, 0.5, 0.83]
+    g.warpFramesBatch(ts, mode)
+    for t in ts:
+        o.warpFrames(t, mode)
+        a, b = out_array(g, hdr), out_array(o, hdr)
+        g.downloadFrame(a)
+        o.downloadFrame(b)
+        assert np.array_equal(a, b), f"t {t}: {np.count_nonzero(a != b)} samples differ"
+
+
+@pytest.mark.parametrize("hdr", [False, True])
 @pytest.mark.parametrize("mode", [0, 1, 2, 3, 5])
 @pytest.mark.parametrize("W,H,maxres,outS", [(256, 144, 270, 0), (130, 70, 35, 144), (320, 176, 88, 0)])
 def test_warp_batch_equals_single_calls(synth, hdr, mode, W, H, maxres, outS):
