@@ -350,16 +350,23 @@ template <int R, int STEP, bool TAPS, int WS> __global__ void __launch_bounds__(
     const int sh = cb - ca;
     const int rb = V0 + minOv + LO;       // first row any candidate reads
     if (staged) {
-        // columns inside the frame: whole rows are copied, rows beyond the top / bottom edge through the mirror
-        // (calcDeltaSumsKernelSDR.h:86-95 reflects each coordinate on its own)
-        const bool colsInside = ca >= 0 && ca + SP <= vw.pitch && cb + RU <= vw.dimU;
-        if (colsInside) {
+        // Whole rows are copied word by word (4 pixels), through the reference's mirror where the region leaves the frame
+        // (calcDeltaSumsKernelSDR.h:86-95 reflects each coordinate on its own): rows by a mirrored row index; a word of four
+        // columns beyond the left / right edge is the aligned word at the reflected position with its pixels reversed —
+        // luma bytes reversed, the two chroma pairs swapped (frame widths that are multiples of 4 keep words from
+        // straddling the edge).
+        const bool colsFast = (vw.dimU & 3) == 0 && ca >= -vw.dimU && ca + SP <= 2 * vw.dimU;
+        if (colsFast) {
             // the region is assembled from the planes: one luma word and one chroma word give four {Y,U,V,0} words
             // (expand4); four rows per iteration keep eight loads of a thread in flight
             const int c4 = tid & 15;
             if (c4 < SP / 4) {
-                const uint8_t* __restrict__ ysrc = vw.y1 + ca + c4 * 4;
-                const uint8_t* __restrict__ csrc = vw.c1 + ca + c4 * 4;
+                const int cc = ca + c4 * 4;
+                const bool rev = cc < 0 || cc >= vw.dimU;
+                const int src = cc < 0 ? -cc - 4 : cc >= vw.dimU ? 2 * vw.dimU - cc - 4 : cc;
+                const uint32_t selY = rev ? 0x0123u : 0x3210u, selC = rev ? 0x1032u : 0x3210u;
+                const uint8_t* __restrict__ ysrc = vw.y1 + src;
+                const uint8_t* __restrict__ csrc = vw.c1 + src;
                 for (int r = tid >> 4; r < RV; r += 64) {
                     uint32_t yw[4], cw[4];
 #pragma unroll
@@ -373,7 +380,7 @@ template <int R, int STEP, bool TAPS, int WS> __global__ void __launch_bounds__(
                         const int rr = r + 16 * i;
                         if (rr < RV) {
                             uint32_t w[4];
-                            expand4(yw[i], cw[i], w);
+                            expand4(__byte_perm(yw[i], 0u, selY), __byte_perm(cw[i], 0u, selC), w);
                             *reinterpret_cast<uint4*>(&s_f1[rr * SP + c4 * 4]) = make_uint4(w[0], w[1], w[2], w[3]);
                         }
                     }
