@@ -666,7 +666,9 @@ def main():
             calc.downloadFrame(out_pinned)
         return len(sched[i])
 
-    POOL = 16
+    E2E_DEPTH = int(os.environ.get("HRB_E2E_DEPTH", "8"))          # downloads left in flight when a step returns
+    E2E_ASYNC_UP = bool(int(os.environ.get("HRB_E2E_ASYNC_UP", "0")))  # upload through update_frame_async (own stream, no host wait)
+    POOL = max(16, E2E_DEPTH + 10)
     out_pool = [torch.empty_like(out_pinned).pin_memory() for _ in range(POOL)]
     pending = []
     dl_count = [0]
@@ -674,7 +676,10 @@ def main():
     def step_e2e(i):
         # same work through the asynchronous entry points: the upload of this frame and the downloads of its outputs
         # overlap the kernels; a consumer takes the delivered frames in order, at most ~one source frame behind
-        calc.updateFrame(pinned[i % RING])
+        if E2E_ASYNC_UP:
+            calc.updateFrameAsync(pinned[i % RING])   # the ring of pinned source frames is 10 deep: no buffer is reused before its upload ended
+        else:
+            calc.updateFrame(pinned[i % RING])
         calc.calculateOpticalFlowAsync()
         if not args.no_batch:
             calc.warpFramesBatch(sched[i], hr.BlendedFrame)
@@ -685,7 +690,7 @@ def main():
                 calc.waitDownload(pending.pop(0))
             pending.append(calc.downloadFrameAsync(out_pool[dl_count[0] % POOL]))
             dl_count[0] += 1
-        while len(pending) > 8:
+        while len(pending) > E2E_DEPTH:
             calc.waitDownload(pending.pop(0))
         return len(sched[i])
 
