@@ -721,8 +721,8 @@ def main():
         for k in range(args.steps):
             frames += step_device(idx)
             idx += 1
-            if k == 31:  # host time to ISSUE a step, taken before the launch queue can push back (the GPU is far behind here)
-                host_issue_ms = (time.perf_counter() - th) * 1e3 / 32
+            if k == 3:  # host time to ISSUE a step: the first four steps, before the handle's ring of four flow records makes the host wait for the GPU
+                host_issue_ms = (time.perf_counter() - th) * 1e3 / 4
         calc.joinFlow()  # the last flow runs on the handle's flow stream: the end event waits for it too
         e1.record(stream)
     calc.synchronize()
