@@ -152,6 +152,18 @@ def bind_near_gpu(local):
         return None
 
 
+def init_dist(local):
+    """NCCL by default (eager, bound to this rank's GPU); HRB_DIST_BACKEND=gloo and HRB_DIST_LAZY=1 exist for A/B runs of the
+    effect of the communicator on the device-timed loop."""
+    import torch
+    import torch.distributed as dist
+    backend = os.environ.get("HRB_DIST_BACKEND", "nccl")
+    if backend == "nccl" and not os.environ.get("HRB_DIST_LAZY"):
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    else:
+        dist.init_process_group(backend)
+
+
 def dist_env():
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -360,7 +372,7 @@ def run_split(args, wl):
     if world > 1:
         bind_near_gpu(local)
     if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        init_dist(local)
     W, H, hdr = wl["W"], wl["H"], wl["hdr"]
     cls = hr.OpticalFlowCalcHDR if hdr else hr.OpticalFlowCalcSDR
     s = SpatialSplitStream(cls, H, W, 8, 6, 0.0, 255.0, wl["maxres"], rank=rank, world_size=world)
@@ -442,7 +454,7 @@ def run_streams(args, wl):
     if world > 1:
         bind_near_gpu(local)
     if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        init_dist(local)
     S = args.streams_per_gpu
     W, H, hdr = wl["W"], wl["H"], wl["hdr"]
     cls = hr.OpticalFlowCalcHDR if hdr else hr.OpticalFlowCalcSDR
@@ -600,7 +612,7 @@ def main():
     if world > 1:
         bind_near_gpu(local)
     if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        init_dist(local)
 
     W, H, hdr = wl["W"], wl["H"], wl["hdr"]
     alg = algorithmic_bytes(wl)
