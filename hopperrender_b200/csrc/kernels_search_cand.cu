@@ -1,15 +1,18 @@
-// kernels_search_cand.cu — search passes for the small windows (2, 4, 8, 16 flow pixels) at full flow resolution:
-// 4 of the 11 iterations at 4K, and the ones where every window has its own offset.
+// kernels_search_cand.cu — search passes for the small windows (2, 4, 8 flow pixels; up to 32 when the tile kernel does
+// not apply) at full flow resolution: the last 3 of the 11 iterations at 4K, where every window has its own offset.
 //
 // The generic kernel fetches frame 1 once per pixel-candidate from global memory: one 64-bit address computation and
-// one L1 transaction per VABSDIFF4.  Here a CTA owns a 32 x 64 tile (u x v, see View) and first looks at the offsets
+// one L1 transaction per VABSDIFF4.  Here a CTA owns a 32 x 128 tile (u x v, see View) and first looks at the offsets
 // of all windows in the tile.  Motion fields are smooth, so they almost always span a few pixels only; the CTA then
 // stages the frame-1 region every candidate of every window of the tile can touch —
-//     (64 + (HI-LO) + spread_v) rows  x  (32 + spread_u) columns  (<= 192 x 48 words) —
-// in shared memory with 16-byte copies, after which a pixel-candidate costs one LDS with an IMMEDIATE offset (the
-// candidate displacement is a compile-time multiple of the row pitch) and one VABSDIFF4.  Tiles at the frame border
-// stage through the mirror; tiles whose offsets spread too far for the buffer fall back to global fetches.  The
-// reduction, arg-min and offset update are those of the generic kernel.
+//     (128 + (HI-LO) + spread_v) rows  x  (32 + spread_u) columns  (<= 254 x 48 pixels) —
+// in shared memory, expanded from the planar planes to one {Y, U, V, 0} word per pixel (expand4), so that ANY displaced
+// pixel is one aligned LDS with an IMMEDIATE offset (the candidate displacement is a compile-time multiple of the row
+// pitch) followed by one VABSDIFF4.  Regions that leave the frame are staged through the reference's mirror without
+// leaving the fast path: mirrored row indices, and words beyond the left / right edge read from the reflected position
+// with their pixels reversed.  Tiles whose offsets spread too far for the buffer fall back to global fetches.
+//   * windows of 2 and 4: one lane owns one window (winGroups): sums, context and arg-min stay in the lane;
+//   * windows of 8 and more: lanes own pixel columns, butterfly reduction, per-window sums in shared memory (candGroups).
 #include <climits>
 
 #include "search_common.cuh"
