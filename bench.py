@@ -255,6 +255,26 @@ class _StdoutToStderr:
         return False
 
 
+_JSON_OUT = None
+
+
+def claim_stdout():
+    """stdout carries ONE JSON line.  Libraries underneath print there too (NCCL's version banner, the reference's device
+    report), so the process's file descriptor 1 is pointed at stderr for its whole life and the line goes to a private
+    duplicate of the original stdout."""
+    global _JSON_OUT
+    if _JSON_OUT is None:
+        sys.stdout.flush()
+        _JSON_OUT = os.fdopen(os.dup(1), "w")
+        os.dup2(2, 1)
+
+
+def emit(line):
+    out = _JSON_OUT or sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
+
+
 def reference_opencl_same_gpu(wl, steps=8, radius=SEARCH_RADIUS):
     with _StdoutToStderr():
         return _reference_opencl_same_gpu(wl, steps, radius)
@@ -336,7 +356,7 @@ def run_reference(args, wl, wl_name):
     if not args.no_cpu_baseline:
         # beside the CPU port: the reference's own kernels on this box's GPU, when its OpenCL leg is usable here
         line["reference_opencl_b200"] = reference_opencl_same_gpu(wl, radius=SEARCH_RADIUS)
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def cpu_baseline(wl):
@@ -430,7 +450,7 @@ def run_split(args, wl):
                     "d2h_bytes_per_step": int(round(frames / args.steps * s.stripe_bytes())), "note": "bytes per rank"},
             "gpu_launches": int(launches),
         }
-        print(json.dumps(line), flush=True)
+        emit(line)
     s.close()
     if world > 1:
         dist.destroy_process_group()
@@ -565,7 +585,7 @@ def run_streams(args, wl):
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(S * calcs[0].inputFrameBytes),
                         "d2h_bytes_per_step": int(round(eframes / esteps * calcs[0].outputFrameBytes)), "steps": esteps},
                 "gpu_launches": int(launches), "clocks": clocks}
-        print(json.dumps(line), flush=True)
+        emit(line)
     for c in calcs:
         c.close()
     if world > 1:
@@ -587,6 +607,7 @@ def main():
     ap.add_argument("--radius", type=int, default=SEARCH_RADIUS)
     ap.add_argument("--streams-per-gpu", type=int, default=1, help="independent video streams (handles) per GPU; >1 prints the multi-stream line")
     args = ap.parse_args()
+    claim_stdout()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     wl = WORKLOADS[args.workload]
     if args.impl == "reference":
@@ -917,7 +938,7 @@ def main():
             # the reference's own OpenCL kernels on this same GPU: the like-for-like numbers are
             # e2e.blocking_api_value vs its value (both blocking APIs) and breakdown_ms_per_step.search vs its ofc_ms
             line["reference_opencl_b200"] = reference_opencl_same_gpu(wl, radius=args.radius)
-        print(json.dumps(line), flush=True)
+        emit(line)
     calc.close()
     if world > 1:
         dist.destroy_process_group()
