@@ -64,11 +64,22 @@ def test_reference_arm_line_has_the_contract_keys():
     res = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "2", "--warmup", "1"],
                          capture_output=True, text=True, timeout=580, env=env, cwd=ROOT)
     assert res.returncode == 0, res.stderr[-2000:]
+    assert len(res.stdout.strip().splitlines()) == 1, "stdout carries the JSON line and nothing else (libraries print to fd 1 too)"
     line = json.loads(res.stdout.strip().splitlines()[-1])
     for k in ("impl", "metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "config", "cpu_baseline", "e2e"):
         assert k in line
     assert line["impl"] == "reference" and line["value"] > 0 and line["cpu_baseline"]["kind"] in ("port", "reference")
     assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["e2e"]["d2h_bytes_per_step"] == 0
+
+
+def test_bench_stdout_is_reserved_for_the_json_line():
+    """claim_stdout points file descriptor 1 at stderr, so text a native library writes to fd 1 cannot land beside the line."""
+    code = ("import os, sys; sys.path.insert(0, %r); import bench; bench.claim_stdout(); os.write(1, b'library banner\\n'); "
+            "print('python print'); bench.emit({'ok': 1})") % ROOT
+    res = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=120, cwd=ROOT)
+    assert res.returncode == 0, res.stderr[-2000:]
+    assert res.stdout == '{"ok": 1}\n'
+    assert "library banner" in res.stderr and "python print" in res.stderr
 
 
 def test_stripe_bounds_are_even_and_tile_the_frame():
